@@ -1,0 +1,238 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE (read-only at /root/reference).
+
+Run once in the build container:  python tests/golden/make_golden.py
+The reference ships no golden vectors of its own, so these files are
+the parity pins for oracle/svae_oracle.py and, through it, for the CUDA path.  The
+reference cannot travel to the GPU box; the .npz files do.
+
+Each case stores: the module state_dicts ("p.<key>", "q.<key>"), the inputs (y, eps, ctf,
+mask, ...), and what the reference returned (elbo, logp, kl, y_hat) plus the gradient of
+-elbo w.r.t. every parameter ("gp.<key>", "gq.<key>").  eps is injected by patching
+Tensor.normal_ for the one (B, I) draw eval_minibatch makes (train_mnist.py:38).
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = os.environ.get("SVAE_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+sys.path.insert(0, REF)
+for name in ("skimage", "skimage.transform", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["skimage.transform"].resize = None
+with contextlib.redirect_stdout(io.StringIO()):
+    import train_mnist, train_particles, train_galaxy          # noqa: E402
+    import spatial_vae.models as ref_models                      # noqa: E402
+    import spatial_vae.ctf as ref_ctf                            # noqa: E402
+
+
+@contextlib.contextmanager
+def inject_eps(eps):
+    orig = torch.Tensor.normal_
+
+    def patched(self, *a, **k):
+        if tuple(self.shape) == tuple(eps.shape):
+            return self.copy_(eps)
+        return orig(self, *a, **k)
+
+    torch.Tensor.normal_ = patched
+    try:
+        yield
+    finally:
+        torch.Tensor.normal_ = orig
+
+
+def build(P_in, z_dim, inf_dim, H, L, Hq, Lq, C, act=nn.Tanh, seed=0):
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = ref_models.SpatialGenerator(z_dim, H, n_out=C, num_layers=L, activation=act)
+        q = ref_models.InferenceNetwork(P_in, inf_dim, Hq, num_layers=Lq, activation=act)
+    return p, q
+
+
+def grid_of(n, m):
+    # verbatim recipe of train_mnist.py:316-320
+    xgrid = np.linspace(-1, 1, m)
+    ygrid = np.linspace(1, -1, n)
+    x0, x1 = np.meshgrid(xgrid, ygrid)
+    return torch.from_numpy(np.stack([x0.ravel(), x1.ravel()], 1)).float()
+
+
+def pack(p, q, extra):
+    d = {}
+    for k, v in p.state_dict().items():
+        d["p." + k] = v.detach().numpy().copy()
+    for k, v in q.state_dict().items():
+        d["q." + k] = v.detach().numpy().copy()
+    for k, v in p.named_parameters():
+        d["gp." + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
+    for k, v in q.named_parameters():
+        d["gq." + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy().copy()
+    for k, v in extra.items():
+        d[k] = v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)
+    return d
+
+
+def mnist_case(name, rotate, translate, act=nn.Tanh, L=2, n=6, m=5, B=5, Z=3, seed=1):
+    P = n * m
+    I = Z + (1 if rotate else 0) + (2 if translate else 0)
+    p, q = build(P, Z, I, 16, L, 12, 2, 1, act, seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    y = (torch.rand(B, P, generator=g) > 0.7).float() * torch.rand(B, P, generator=g)
+    eps = torch.randn(B, I, generator=g)
+    x = grid_of(n, m)
+    with inject_eps(eps):
+        elbo, logp, kl, y_hat = train_mnist.eval_minibatch(x, y, p, q, rotate=rotate, translate=translate,
+                                                          dx_scale=0.1, theta_prior=np.pi / 4)
+    (-elbo).backward()
+    d = pack(p, q, dict(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, y_hat=y_hat,
+                        n=n, m=m, rotate=int(rotate), translate=int(translate), L=L,
+                        theta_prior=np.pi / 4, dx_scale=0.1,
+                        act="tanh" if act is nn.Tanh else "leakyrelu"))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def particles_case(name, fit_noise=False, use_ctf=False, use_mask=False, augment=False, z_scale=1.0,
+                   n=6, B=4, Z=2, seed=2):
+    P = n * n
+    I = Z + 3
+    C = 2 if fit_noise else 1
+    p, q = build(P, Z, I, 16, 2, 12, 2, C, nn.Tanh, seed)
+    g = torch.Generator().manual_seed(200 + seed)
+    y = torch.randn(B, P, generator=g)
+    eps = torch.randn(B, I, generator=g)
+    x = grid_of(n, n)
+    ctf = None
+    if use_ctf:
+        ctf = 0.05 * torch.randn(B, 1, n - 1, n - 1, generator=g)
+    mask = None
+    if use_mask:  # recipe of train_particles.py:387-396
+        radius = n / 2
+        yy, xx = np.ogrid[:n, :n]
+        dist = np.sqrt((n / 2 - yy) ** 2 + (n / 2 - xx) ** 2)
+        mask = (torch.from_numpy(dist) < radius).view(-1)
+    extra = {}
+    if augment:
+        from PIL import Image
+        np.random.seed(7)
+        offset = np.random.uniform(0, 2 * np.pi, size=B)
+        y_rot = y.clone()
+        for i in range(B):
+            im = Image.fromarray(y[i].view(n, n).numpy())
+            im = im.rotate(360 * offset[i] / 2 / np.pi, resample=Image.BICUBIC)
+            y_rot[i] = torch.from_numpy(np.array(im)).view(-1)
+        extra = dict(theta_offset=offset.astype(np.float32), y_enc=y_rot)
+        np.random.seed(7)  # the reference draws the same offsets
+    with inject_eps(eps):
+        elbo, logp, kl = train_particles.eval_minibatch(x, y, mask, ctf, p, q, rotate=True, translate=True,
+                                                       dx_scale=0.1, theta_prior=np.pi,
+                                                       augment_rotation=augment, z_scale=z_scale)
+    (-elbo).backward()
+    extra.update(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, n=n, z_scale=z_scale,
+                 fit_noise=int(fit_noise), theta_prior=np.pi, dx_scale=0.1)
+    if ctf is not None:
+        extra["ctf"] = ctf
+    if mask is not None:
+        extra["mask"] = mask
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(p, q, extra))
+
+
+def galaxy_case(name, n=4, B=3, Z=4, L=3, seed=3, z_scale=1.0):
+    P = n * n
+    I = Z + 3
+    p, q = build(P * 3, Z, I, 16, L, 20, 2, 3, nn.Tanh, seed)
+    g = torch.Generator().manual_seed(300 + seed)
+    y = torch.rand(B, P, 3, generator=g)
+    eps = torch.randn(B, I, generator=g)
+    x = grid_of(n, n)
+    with inject_eps(eps):
+        elbo, logp, kl, y_hat = train_galaxy.eval_minibatch(x, y, p, q, rotate=True, translate=True,
+                                                           dx_scale=0.1, theta_prior=np.pi, z_scale=z_scale)
+    (-elbo).backward()
+    d = pack(p, q, dict(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, y_hat=y_hat, n=n, L=L,
+                        z_scale=z_scale, theta_prior=np.pi, dx_scale=0.1))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def trajectory_case(name, steps=10, n=6, m=6, B=8, Z=3, seed=4):
+    """10 reference train steps (eval_minibatch, backward, Adam.step, zero_grad) with the
+    reference's optimiser construction (train_mnist.py:387-392, 147-150)."""
+    P = n * m
+    I = Z + 3
+    p, q = build(P, Z, I, 16, 2, 12, 2, 1, nn.Tanh, seed)
+    init = {"p." + k: v.detach().numpy().copy() for k, v in p.state_dict().items()}
+    init.update({"q." + k: v.detach().numpy().copy() for k, v in q.state_dict().items()})
+    optim = torch.optim.Adam(list(p.parameters()) + list(q.parameters()), lr=1e-4)
+    g = torch.Generator().manual_seed(400 + seed)
+    x = grid_of(n, m)
+    ys, es, elbos = [], [], []
+    for _ in range(steps):
+        y = (torch.rand(B, P, generator=g) > 0.7).float() * torch.rand(B, P, generator=g)
+        eps = torch.randn(B, I, generator=g)
+        with inject_eps(eps):
+            elbo, _, _, _ = train_mnist.eval_minibatch(x, y, p, q, rotate=True, translate=True,
+                                                       dx_scale=0.1, theta_prior=np.pi / 4)
+        (-elbo).backward()
+        optim.step()
+        optim.zero_grad()
+        ys.append(y.numpy())
+        es.append(eps.numpy())
+        elbos.append(float(elbo))
+    d = {"init." + k: v for k, v in init.items()}
+    for k, v in p.state_dict().items():
+        d["final.p." + k] = v.detach().numpy().copy()
+    for k, v in q.state_dict().items():
+        d["final.q." + k] = v.detach().numpy().copy()
+    d.update(ys=np.stack(ys), eps=np.stack(es), elbos=np.array(elbos), grid=x.numpy(), n=n, m=m,
+             theta_prior=np.pi / 4, dx_scale=0.1, lr=1e-4)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def decoder_case(name, n=5, m=7, B=3, Z=4, L=3, C=2, seed=5):
+    """Module-level SpatialGenerator.forward on explicit coordinates (models.py:90-132)."""
+    p, _ = build(n * m, Z, Z, 16, L, 8, 1, C, nn.Tanh, seed)
+    g = torch.Generator().manual_seed(500 + seed)
+    x = torch.randn(B, n * m, 2, generator=g)
+    z = torch.randn(B, Z, generator=g)
+    y = p(x, z)
+    d = {"p." + k: v.detach().numpy().copy() for k, v in p.state_dict().items()}
+    d.update(x=x.numpy(), z=z.numpy(), y_hat=y.detach().numpy(), L=L)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def ctf_case(name, N=3, n=7, m=7):
+    import pandas as pd
+    rng = np.random.default_rng(11)
+    tab = pd.DataFrame(dict(defocus=rng.uniform(1, 3, N), cs=np.full(N, 2.7), voltage=np.full(N, 300.0),
+                            apix=np.full(N, 2.5), bfactor=np.full(N, 100.0), ampcont=np.full(N, 10.0),
+                            dfdiff=np.zeros(N), dfang=rng.uniform(0, 180, N)))
+    k = ref_ctf.ctf_filter(tab, n, m)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kernels=k, n=n, m=m,
+                        **{c: tab[c].to_numpy() for c in tab.columns})
+
+
+if __name__ == "__main__":
+    mnist_case("mnist_rt", True, True)
+    mnist_case("mnist_r", True, False, seed=11)
+    mnist_case("mnist_t", False, True, seed=12)
+    mnist_case("mnist_none", False, False, seed=13)
+    mnist_case("mnist_leaky_L3", True, True, act=nn.LeakyReLU, L=3, seed=14)
+    particles_case("particles_plain")
+    particles_case("particles_fitnoise", fit_noise=True, seed=21)
+    particles_case("particles_ctf", use_ctf=True, seed=22)
+    particles_case("particles_mask", use_mask=True, seed=23)
+    particles_case("particles_augment", augment=True, seed=24)
+    particles_case("particles_zscale0", z_scale=0.0, seed=25)
+    galaxy_case("galaxy_rgb")
+    trajectory_case("mnist_adam10")
+    decoder_case("decoder_module")
+    ctf_case("ctf_kernels")
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
