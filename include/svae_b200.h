@@ -1,0 +1,183 @@
+/*
+ * svae_b200.h -- C ABI of libsvae_b200.so: the spatial-VAE training-step hot path on B200 (sm_100a).
+ *
+ * The reference (cfframe/spatial-VAE) is pure Python on PyTorch and defines no native ABI, so
+ * these entry points are what a binding for this path replaces, one per reference call site
+ * (paths relative to the reference checkout):
+ *
+ *   svae_encoder_forward / _backward   InferenceNetwork.forward             spatial_vae/models.py:46-54
+ *   svae_decoder_forward / _backward   SpatialGenerator.forward             spatial_vae/models.py:90-132
+ *   svae_step                          eval_minibatch + loss.backward()     train_mnist.py:24-90,147-148
+ *                                                                           train_particles.py:22-148,178-179
+ *                                                                           train_galaxy.py:27-128,207-208
+ *   svae_adam_step                     optim.step(); optim.zero_grad()      train_mnist.py:149-150 (Adam :389-392)
+ *   svae_gather_rows                   DataLoader(TensorDataset, shuffle)   train_mnist.py:334,395-396
+ *   svae_gemm_bf16                     one nn.Linear of SpatialGenerator.layers (models.py:82,126) on
+ *                                      tcgen05 tensor cores (building block, exposed for tests)
+ *
+ * Conventions
+ *   - plain C, no torch types: raw DEVICE pointers, sizes, a cudaStream_t passed as void*.
+ *   - the caller owns every buffer (parameters, gradients, Adam state, inputs, outputs, workspace);
+ *     the library never allocates device memory, never retains pointers, never synchronises:
+ *     all work is enqueued on `stream` (CUDA-graph capturable).
+ *   - every entry returns 0 on success or a negative SVAE_E* code; svae_last_error() gives text.
+ *   - there is NO CPU fallback: without a CUDA device the calls fail with SVAE_ECUDA.
+ *   - tensors are row-major fp32 unless stated; weights use nn.Linear layout (out_features, in_features).
+ */
+#ifndef SVAE_B200_H
+#define SVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVAE_OK       0
+#define SVAE_EINVAL  (-1)   /* unsupported shape / flag combination (text in svae_last_error) */
+#define SVAE_EALIGN  (-2)   /* a pointer or leading dimension violates an alignment rule      */
+#define SVAE_ECUDA   (-3)   /* CUDA runtime/driver error                                      */
+#define SVAE_ENOSPACE (-4)  /* workspace too small                                            */
+
+#define SVAE_MAX_LAYERS 8
+
+/* activation codes: nn.Tanh, nn.LeakyReLU(0.01), nn.ReLU, nn.Sigmoid (train_galaxy.py:426-434) */
+enum { SVAE_ACT_TANH = 0, SVAE_ACT_LEAKYRELU = 1, SVAE_ACT_RELU = 2, SVAE_ACT_SIGMOID = 3 };
+/* likelihoods: Bernoulli (train_mnist.py:80-81), Gaussian unit variance and Gaussian with the
+ * learned ("fit-noise") variance (train_particles.py:136-139) */
+enum { SVAE_LIK_BERNOULLI = 0, SVAE_LIK_GAUSS = 1, SVAE_LIK_GAUSS_FITNOISE = 2 };
+/* precision of the decoder hidden-layer GEMMs:
+ *   PARITY  fp32 FFMA kernels everywhere (bit-for-bit comparable with the fp32 reference up to
+ *           summation order);
+ *   FAST    bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulation; first layer, output
+ *           layer, likelihood, KL, reductions, encoder, dW accumulation and Adam stay fp32. */
+enum { SVAE_PRECISION_PARITY = 0, SVAE_PRECISION_FAST = 1 };
+
+typedef struct {
+    int32_t B;        /* images in this call (this rank's slice of the minibatch)              */
+    int32_t P;        /* coordinate rows per image (n_rows * n_cols)                           */
+    int32_t n_rows;   /* image height (only used by the CTF correlation)                       */
+    int32_t n_cols;   /* image width                                                           */
+    int32_t C;        /* decoder n_out: 1, 2 (fit-noise) or 3 (RGB)                            */
+    int32_t Cin;      /* channels per pixel seen by the encoder; encoder input = P * Cin       */
+    int32_t Z;        /* unstructured latent dimension                                         */
+    int32_t I;        /* inference dimension = Z + rotate + 2*translate                        */
+    int32_t H;        /* decoder hidden width                                                  */
+    int32_t L;        /* decoder num_layers: L-1 hidden HxH Linears (models.py:78-83)          */
+    int32_t Hq;       /* encoder hidden width                                                  */
+    int32_t Lq;       /* encoder num_layers: Lq hidden Linears, then the 2*I head (models.py:31-41) */
+    int32_t k_ctf;    /* CTF kernel side length, 0 = no CTF (train_particles.py:112-119)       */
+} SvaeShape;
+
+typedef struct {
+    int32_t rotate;          /* latent column 0 is theta (train_mnist.py:42-59)                */
+    int32_t translate;       /* next two columns are dx (train_mnist.py:65-74)                 */
+    int32_t likelihood;      /* SVAE_LIK_*                                                     */
+    int32_t theta_kl_mean;   /* 1: mnist theta-KL with mean penalty (train_mnist.py:63); 0: particles/galaxy */
+    int32_t activation;      /* SVAE_ACT_*                                                     */
+    int32_t precision;       /* SVAE_PRECISION_*                                               */
+    int32_t softplus;        /* softplus on output channel 0 after the sigmoid (models.py:129-130) */
+    int32_t chunk_images;    /* images per decoder pass (bounds the activation workspace); 0 = library default */
+    float   theta_prior;     /* std of the rotation prior                                      */
+    float   dx_scale;        /* std of the translation prior                                   */
+    float   z_scale;         /* multiplies z only (train_particles.py:99); mnist: 1            */
+    float   grad_scale;      /* 1 / (global minibatch size): gradients are of -mean_b(elbo_b)  */
+} SvaeConfig;
+
+/* SpatialGenerator parameters (models.py:69-87). Gradient structs use the same layout. */
+typedef struct {
+    float* coord_w;                       /* (H, 2)  coord_linear.weight                       */
+    float* coord_b;                       /* (H)     coord_linear.bias                         */
+    float* latent_w;                      /* (H, Z)  latent_linear.weight, NULL when Z == 0    */
+    float* hidden_w[SVAE_MAX_LAYERS];     /* (H, H)  layers.{1,3,..}.weight, L-1 entries       */
+    float* hidden_b[SVAE_MAX_LAYERS];     /* (H)                                               */
+    float* out_w;                         /* (C, H)  last Linear                               */
+    float* out_b;                         /* (C)                                               */
+} SvaeDecoderParams;
+
+/* InferenceNetwork parameters (models.py:31-41): Lq hidden Linears then the head (2I, Hq). */
+typedef struct {
+    float* w[SVAE_MAX_LAYERS + 1];
+    float* b[SVAE_MAX_LAYERS + 1];
+} SvaeEncoderParams;
+
+/* Inputs of one eval_minibatch. */
+typedef struct {
+    const float* grid;          /* (P, 2) pixel coordinates (train_mnist.py:316-320)             */
+    const float* y;             /* (B, P*C_target) targets; C_target = Cin                       */
+    const float* y_enc;         /* (B, P*Cin) what the encoder sees; NULL = y (augmentation, train_particles.py:28-50) */
+    const float* theta_offset;  /* (B) added to theta before rotating (train_particles.py:71-74); may be NULL */
+    const float* eps;           /* (B, I) the N(0,1) draw of train_mnist.py:38                   */
+    const float* ctf;           /* (B, k_ctf, k_ctf) real-space kernels or NULL                  */
+    const uint8_t* mask;        /* (P) 0/1 pixel mask or NULL (train_particles.py:126-132)       */
+} SvaeStepInputs;
+
+/* Outputs of one eval_minibatch (all optional except stats). */
+typedef struct {
+    float* stats;        /* (B, 3): per image [logp_i, kl_i, elbo_i]; the reference's scalars are their batch means */
+    float* y_hat;        /* (B, P, C) decoder output or NULL                                   */
+    float* latent;       /* (B, I) sampled latent or NULL                                      */
+} SvaeStepOutputs;
+
+int  svae_version(void);
+/* copies the last error text of the calling thread into buf (NUL terminated); returns its length */
+int  svae_last_error(char* buf, int n);
+/* number of SMs of the current device, <0 on error (used by the host to size row chunks) */
+int  svae_device_sm_count(void);
+
+/* Bytes of caller-provided scratch svae_step / svae_decoder_* need for this shape+config. */
+int  svae_workspace_bytes(const SvaeShape* shape, const SvaeConfig* cfg, size_t* bytes);
+
+/* InferenceNetwork.forward: x (B, P*Cin) -> out (B, 2I) = [z_mu | z_logstd].
+ * acts: scratch (Lq, B, Hq) receiving the hidden activations (needed by the backward). */
+int  svae_encoder_forward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params,
+                          const float* x, float* out, float* acts, void* stream);
+/* Backward of the above: g_out (B, 2I) is overwritten as scratch; grads are ACCUMULATED (+=)
+ * into `grads` (zero them first); g_x (B, P*Cin) optional. scratch: (2, B, Hq) floats. */
+int  svae_encoder_backward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params,
+                           const float* x, const float* acts, float* g_out, SvaeEncoderParams* grads,
+                           float* g_x, float* scratch, void* stream);
+
+/* SpatialGenerator.forward on explicit coordinates: x (B, P, 2), z (B, Z) -> y_hat (B, P, C). */
+int  svae_decoder_forward(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderParams* params,
+                          const float* x, const float* z, float* y_hat, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* Backward of the above given g_y (B, P, C) = dLoss/dy_hat: accumulates parameter gradients
+ * into `grads`, writes g_x (B, P, 2) and g_z (B, Z) when non-NULL. Re-runs the forward. */
+int  svae_decoder_backward(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderParams* params,
+                           const float* x, const float* z, const float* g_y, SvaeDecoderParams* grads,
+                           float* g_x, float* g_z, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One eval_minibatch: encoder -> reparameterise -> rotate/translate -> decoder -> ELBO.
+ * When dec_grads/enc_grads are non-NULL also the backward of -grad_scale * sum_b elbo_b,
+ * ACCUMULATED into the gradient buffers (zero them, or keep them for gradient accumulation). */
+int  svae_step(const SvaeShape* shape, const SvaeConfig* cfg,
+               const SvaeDecoderParams* dec, const SvaeEncoderParams* enc,
+               const SvaeStepInputs* in, const SvaeStepOutputs* out,
+               SvaeDecoderParams* dec_grads, SvaeEncoderParams* enc_grads,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, no weight decay, no amsgrad);
+ * t is the 1-based step count; zero_grad != 0 clears the gradient afterwards (optim.zero_grad()). */
+int  svae_adam_step(float* param, float* grad, float* m, float* v, size_t n,
+                    float lr, float beta1, float beta2, float eps, int t, int zero_grad, void* stream);
+
+/* dst[i, :] = src[index[i], :] for i < n_rows: one launch replaces the per-sample DataLoader fetch. */
+int  svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
+                      void* stream);
+
+/* bf16 tensor-core GEMM building blocks (tcgen05 / TMEM / TMA), fp32 accumulation.
+ *   mode 0  FWD : out[M,N]  = act(A[M,K] * W[N,K]^T + bias[N])                   (bf16 out)
+ *   mode 1  DX  : out[M,N]  = (A[M,K] * W[K,N]) .* act'(aux[M,N])                (bf16 out)
+ *   mode 2  DW  : outf[M,N] += A[Kr,M]^T * Bm[Kr,N]   (fp32 out, accumulated with atomics)
+ * All bf16 matrices are row-major with leading dimension ld* (elements, multiple of 8). */
+int  svae_gemm_bf16(int mode, int M, int N, int K,
+                    const void* A, int lda, const void* W, int ldw,
+                    const float* bias, const void* aux, int ldaux, int activation,
+                    void* out, int ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVAE_B200_H */

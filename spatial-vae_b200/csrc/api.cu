@@ -1,0 +1,547 @@
+// C-ABI entry points of libsvae_b200.so and the host-side orchestration of one step.
+// See include/svae_b200.h for the contract and the reference call sites each entry replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "kernels.cuh"
+
+namespace svae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return SVAE_ECUDA;
+}
+
+// ---- workspace plan ------------------------------------------------------------------------------
+struct Plan {
+    int Hp = 0;            // padded hidden width (row stride of the activation matrices)
+    int chunk = 0;         // images per decoder pass
+    size_t esize = 4;      // bytes per activation element
+    size_t total = 0;
+    // offsets (bytes)
+    size_t enc_acts, zo, enc_scratch, lat, img, zs, hz, S, dz, g_zo, o, g_o, acts, delta, wbf16;
+    size_t act_stride = 0, delta_stride = 0, w_stride = 0;
+};
+
+static size_t take(size_t& cur, size_t bytes) {
+    size_t off = cur;
+    cur += (bytes + 1023) / 1024 * 1024;
+    return off;
+}
+
+static int validate(const SvaeShape& s, const SvaeConfig& c) {
+    SVAE_REQUIRE(s.B >= 0 && s.P > 0 && s.H > 0 && s.L >= 1 && s.L <= SVAE_MAX_LAYERS, SVAE_EINVAL,
+                 "bad shape: B=%d P=%d H=%d L=%d", s.B, s.P, s.H, s.L);
+    SVAE_REQUIRE(s.C >= 1 && s.C <= 4, SVAE_EINVAL, "n_out=%d not supported (1..4)", s.C);
+    SVAE_REQUIRE(s.Z >= 0 && s.I == s.Z + (c.rotate ? 1 : 0) + (c.translate ? 2 : 0), SVAE_EINVAL,
+                 "inference dim %d != z_dim %d + rotate + 2*translate", s.I, s.Z);
+    SVAE_REQUIRE(c.activation >= 0 && c.activation <= 3, SVAE_EINVAL, "unknown activation %d", c.activation);
+    SVAE_REQUIRE(c.precision == SVAE_PRECISION_PARITY || c.precision == SVAE_PRECISION_FAST, SVAE_EINVAL,
+                 "unknown precision %d", c.precision);
+    if (c.likelihood == SVAE_LIK_GAUSS_FITNOISE) {
+        SVAE_REQUIRE(s.C == 2, SVAE_EINVAL, "fit-noise needs n_out == 2 (train_particles.py:447-449)");
+        // the reference's variance convolution lacks groups= and crashes (train_particles.py:121-124,137)
+        SVAE_REQUIRE(s.k_ctf == 0, SVAE_EINVAL, "CTF with fit-noise is rejected by the reference");
+    } else if (c.likelihood == SVAE_LIK_GAUSS) {
+        SVAE_REQUIRE(s.C == 1, SVAE_EINVAL, "Gaussian likelihood needs n_out == 1");
+        if (s.k_ctf > 0)
+            SVAE_REQUIRE((s.k_ctf & 1) && s.n_rows * s.n_cols == s.P, SVAE_EINVAL,
+                         "CTF kernels must be odd-sized and n_rows*n_cols == P");
+    } else {
+        SVAE_REQUIRE(c.likelihood == SVAE_LIK_BERNOULLI, SVAE_EINVAL, "unknown likelihood %d", c.likelihood);
+        SVAE_REQUIRE(s.k_ctf == 0, SVAE_EINVAL, "CTF only applies to the Gaussian likelihood");
+    }
+    return SVAE_OK;
+}
+
+static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
+    const bool fast = (c.precision == SVAE_PRECISION_FAST);
+    p.Hp = fast ? (int)round_up(s.H, 64) : (int)round_up(s.H, 2);
+    p.esize = fast ? 2 : 4;
+    int chunk = c.chunk_images;
+    if (chunk <= 0) {
+        // bound the activation workspace (L act + 2 delta matrices) to ~6 GiB per pass
+        const double per_image = (double)s.P * p.Hp * p.esize * (s.L + 2);
+        chunk = (int)fmax(1.0, floor(6.0 * 1024 * 1024 * 1024 / per_image));
+    }
+    if (chunk > s.B) chunk = s.B;
+    if (chunk < 1) chunk = 1;
+    p.chunk = chunk;
+    const size_t B = (size_t)(s.B > 0 ? s.B : 1), I = (size_t)s.I, rows = (size_t)chunk * s.P;
+    size_t cur = 0;
+    p.enc_acts = take(cur, (size_t)s.Lq * B * s.Hq * 4);
+    p.zo = take(cur, B * 2 * I * 4);
+    const size_t wide = (size_t)(s.Hq > 2 * s.I ? s.Hq : 2 * s.I);
+    p.enc_scratch = take(cur, 2 * B * wide * 4);
+    p.lat = take(cur, B * I * 4);
+    p.img = take(cur, B * 4 * 4);
+    p.zs = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
+    p.hz = take(cur, B * p.Hp * 4);
+    p.S = take(cur, B * 3 * p.Hp * 4);
+    p.dz = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
+    p.g_zo = take(cur, B * 2 * I * 4);
+    p.o = take(cur, rows * s.C * 4);
+    p.g_o = take(cur, rows * s.C * 4);
+    p.act_stride = (rows * p.Hp * p.esize + 1023) / 1024 * 1024;
+    p.acts = take(cur, p.act_stride * s.L);
+    p.delta_stride = p.act_stride;
+    p.delta = take(cur, p.delta_stride * 2);
+    p.w_stride = (size_t)p.Hp * p.Hp * 2;
+    p.wbf16 = take(cur, fast ? p.w_stride * (s.L > 1 ? s.L - 1 : 1) : 0);
+    p.total = cur;
+    return SVAE_OK;
+}
+
+// ---- encoder -------------------------------------------------------------------------------------
+static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x, float* out,
+                                float* acts, cudaStream_t st) {
+    const int n_in = s.P * s.Cin;
+    const float* cur = x;
+    int k = n_in;
+    for (int l = 0; l < s.Lq; ++l) {
+        SgemmArgs a{};
+        a.A = cur; a.sAm = k; a.sAk = 1;
+        a.B = q.w[l]; a.sBk = 1; a.sBn = k;
+        float* dst = acts + (size_t)l * s.B * s.Hq;
+        a.C = dst; a.ldc = s.Hq;
+        a.M = s.B; a.N = s.Hq; a.K = k;
+        a.bias = q.b[l]; a.act = act;
+        SVAE_TRY(sgemm(a, st));
+        cur = dst; k = s.Hq;
+    }
+    SgemmArgs a{};
+    a.A = cur; a.sAm = k; a.sAk = 1;
+    a.B = q.w[s.Lq]; a.sBk = 1; a.sBn = k;
+    a.C = out; a.ldc = 2 * s.I;
+    a.M = s.B; a.N = 2 * s.I; a.K = k;
+    a.bias = q.b[s.Lq];
+    return sgemm(a, st);
+}
+
+// g_out (B,2I) is the gradient w.r.t. the head output; scratch holds two (B, max(Hq,2I)) buffers.
+static int encoder_backward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x,
+                                 const float* acts, const float* g_out, SvaeEncoderParams& gq, float* g_x,
+                                 float* scratch, cudaStream_t st) {
+    const int n_in = s.P * s.Cin;
+    const size_t wide = (size_t)(s.Hq > 2 * s.I ? s.Hq : 2 * s.I);
+    float* buf[2] = {scratch, scratch + (size_t)s.B * wide};
+    const float* g = g_out;
+    int gn = 2 * s.I;                      // width of g
+    int split = s.B >= 2048 ? 8 : (s.B >= 512 ? 4 : 1);
+    for (int l = s.Lq; l >= 0; --l) {
+        const float* a_in = (l == 0) ? x : acts + (size_t)(l - 1) * s.B * s.Hq;
+        const int k_in = (l == 0) ? n_in : s.Hq;
+        // dW[l] (gn, k_in) += g^T a_in
+        SgemmArgs w{};
+        w.A = g; w.sAm = 1; w.sAk = gn;
+        w.B = a_in; w.sBk = k_in; w.sBn = 1;
+        w.C = gq.w[l]; w.ldc = k_in;
+        w.M = gn; w.N = k_in; w.K = s.B;
+        w.accumulate = 1; w.split_k = split;
+        SVAE_TRY(sgemm(w, st));
+        SVAE_TRY(col_sum<float>(g, s.B, gn, gn, gq.b[l], st));
+        if (l == 0 && g_x == nullptr) break;
+        // g_in (B, k_in) = (g W[l]) .* act'(a_in)
+        SgemmArgs d{};
+        d.A = g; d.sAm = gn; d.sAk = 1;
+        d.B = q.w[l]; d.sBk = k_in; d.sBn = 1;
+        float* dst = (l == 0) ? g_x : buf[l & 1];
+        d.C = dst; d.ldc = k_in;
+        d.M = s.B; d.N = k_in; d.K = gn;
+        if (l > 0) { d.dsrc = a_in; d.ld_dsrc = k_in; d.dact = act; }
+        SVAE_TRY(sgemm(d, st));
+        g = dst; gn = k_in;
+    }
+    return SVAE_OK;
+}
+
+// ---- decoder passes over one chunk of images -----------------------------------------------------
+template <typename T>
+struct DecoderCtx {
+    const SvaeShape* s;
+    const SvaeConfig* c;
+    const Plan* p;
+    char* ws;
+    cudaStream_t st;
+    T* act(int l) const { return reinterpret_cast<T*>(ws + p->acts + p->act_stride * l); }
+    T* delta(int i) const { return reinterpret_cast<T*>(ws + p->delta + p->delta_stride * i); }
+    float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+    __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
+};
+
+template <typename T>
+static int hidden_forward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, int l, int rows);
+template <>
+int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, int l, int rows) {
+    const int H = d.s->H, Hp = d.p->Hp;
+    SgemmArgs a{};
+    a.A = d.act(l - 1); a.sAm = Hp; a.sAk = 1;
+    a.B = dp.hidden_w[l - 1]; a.sBk = 1; a.sBn = H;
+    a.C = d.act(l); a.ldc = Hp;
+    a.M = rows; a.N = H; a.K = H;
+    a.bias = dp.hidden_b[l - 1]; a.act = d.c->activation;
+    return sgemm(a, d.st);
+}
+template <>
+int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp, int l, int rows) {
+    const int Hp = d.p->Hp;
+    return tc_gemm(0, rows, Hp, Hp, d.act(l - 1), Hp, d.wbf(l - 1), Hp, dp.hidden_b[l - 1], d.s->H, nullptr, 0,
+                   d.c->activation, d.act(l), Hp, d.st);
+}
+
+template <typename T>
+static int hidden_backward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l, int rows,
+                           const T* delta, T* delta_prev);
+template <>
+int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l,
+                           int rows, const float* delta, float* delta_prev) {
+    const int H = d.s->H, Hp = d.p->Hp;
+    // dW_l (H,H) += delta^T act[l-1]
+    SgemmArgs w{};
+    w.A = delta; w.sAm = 1; w.sAk = Hp;
+    w.B = d.act(l - 1); w.sBk = Hp; w.sBn = 1;
+    w.C = g.hidden_w[l - 1]; w.ldc = H;
+    w.M = H; w.N = H; w.K = rows;
+    w.accumulate = 1;
+    const int tiles = ceil_div(H, 128) * ceil_div(H, 128);
+    w.split_k = max(1, min(ceil_div(rows, 256), ceil_div(2 * 148, tiles)));
+    SVAE_TRY(sgemm(w, d.st));
+    // delta_prev = (delta W_l) .* act'(act[l-1])
+    SgemmArgs x{};
+    x.A = delta; x.sAm = Hp; x.sAk = 1;
+    x.B = dp.hidden_w[l - 1]; x.sBk = H; x.sBn = 1;
+    x.C = delta_prev; x.ldc = Hp;
+    x.M = rows; x.N = H; x.K = H;
+    x.dsrc = d.act(l - 1); x.ld_dsrc = Hp; x.dact = d.c->activation;
+    return sgemm(x, d.st);
+}
+template <>
+int hidden_backward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp,
+                                   SvaeDecoderParams& g, int l, int rows, const __nv_bfloat16* delta,
+                                   __nv_bfloat16* delta_prev) {
+    const int H = d.s->H, Hp = d.p->Hp;
+    (void)dp;
+    // dW_l (H,H; ld H) += delta^T act[l-1]   (fp32 accumulate, atomics across row splits)
+    SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
+    return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
+                   delta_prev, Hp, d.st);
+}
+
+// forward of the decoder over images [b0, b0+nb): fills act[0..L-1] and logits o; optional y_hat
+template <typename T>
+static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, int b0, int nb,
+                                 const float* grid, const float* x_explicit, float* y_hat) {
+    const SvaeShape& s = *d.s;
+    const int Hp = d.p->Hp, rows = nb * s.P;
+    if (rows == 0) return SVAE_OK;
+    if (std::is_same<T, float>::value && Hp != s.H) {
+        SVAE_CUDA(cudaMemsetAsync(d.ws + d.p->acts, 0, d.p->act_stride * s.L + d.p->delta_stride * 2, d.st));
+    }
+    SVAE_TRY(layer0_forward<T>(s, d.c->activation, b0, nb, dp.coord_w, d.f(d.p->hz), grid, d.f(d.p->img), x_explicit,
+                               s.H, Hp, d.act(0), d.st));
+    for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows));
+    return out_forward<T>(d.act(s.L - 1), rows, s.H, Hp, s.C, dp.out_w, dp.out_b, d.c->softplus, d.f(d.p->o),
+                          y_hat ? y_hat + (size_t)b0 * s.P * s.C : nullptr, d.st);
+}
+
+// backward over the same chunk given g_o (rows, C) in the workspace: parameter grads, S[b0..]
+template <typename T>
+static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int b0,
+                                  int nb, const float* grid, const float* x_explicit, float* g_x) {
+    const SvaeShape& s = *d.s;
+    const int Hp = d.p->Hp, rows = nb * s.P;
+    if (rows == 0) return SVAE_OK;
+    int cur = 0;
+    SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.f(d.p->g_o), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
+                             g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
+    for (int l = s.L - 1; l >= 1; --l) {
+        SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1)));
+        cur ^= 1;
+        if (l - 1 >= 1) SVAE_TRY(col_sum<T>(d.delta(cur), rows, s.H, Hp, g.hidden_b[l - 2], d.st));
+    }
+    SVAE_TRY(image_col_reduce<T>(d.delta(cur), b0, nb, s.P, Hp, grid, x_explicit, d.f(d.p->S), d.st));
+    if (g_x) SVAE_TRY(coord_row_grad<T>(d.delta(cur), rows, s.H, Hp, dp.coord_w, g_x + (size_t)b0 * s.P * 2, d.st));
+    return SVAE_OK;
+}
+
+static int prepare_bf16_weights(const SvaeShape& s, const Plan& p, const SvaeDecoderParams& dp, char* ws,
+                                cudaStream_t st) {
+    for (int l = 0; l < s.L - 1; ++l) {
+        SVAE_TRY(to_bf16_padded(dp.hidden_w[l], s.H, s.H,
+                                reinterpret_cast<__nv_bfloat16*>(ws + p.wbf16 + p.w_stride * l), p.Hp, p.Hp, st));
+    }
+    return SVAE_OK;
+}
+
+// hz (B,Hp) = zs Wz^T + coord_b
+static int latent_projection(const SvaeShape& s, const Plan& p, const SvaeDecoderParams& dp, const float* zs,
+                             float* hz, cudaStream_t st) {
+    if (s.B == 0) return SVAE_OK;
+    if (s.Z > 0 && dp.latent_w != nullptr) {
+        SgemmArgs a{};
+        a.A = zs; a.sAm = s.Z; a.sAk = 1;
+        a.B = dp.latent_w; a.sBk = 1; a.sBn = s.Z;
+        a.C = hz; a.ldc = p.Hp;
+        a.M = s.B; a.N = s.H; a.K = s.Z;
+        a.bias = dp.coord_b;
+        return sgemm(a, st);
+    }
+    return fill_rows(hz, dp.coord_b, s.B, s.H, p.Hp, st);
+}
+
+// gradients that flow through S: coord layer, latent_linear, and dz (B,Z)
+static int first_layer_param_grads(const SvaeShape& s, const SvaeConfig& c, const Plan& p,
+                                   const SvaeDecoderParams& dp, SvaeDecoderParams& g, const float* S,
+                                   const float* img, const float* zs, float z_scale, int explicit_x, float* dz,
+                                   cudaStream_t st) {
+    (void)c;
+    if (s.B == 0) return SVAE_OK;
+    SVAE_TRY(coord_param_grad(S, img, s.B, s.H, p.Hp, explicit_x, g.coord_w, g.coord_b, st));
+    if (s.Z > 0 && dp.latent_w != nullptr) {
+        // dWz (H,Z) += S_s^T zs
+        SgemmArgs w{};
+        w.A = S; w.sAm = 1; w.sAk = 3L * p.Hp;
+        w.B = zs; w.sBk = s.Z; w.sBn = 1;
+        w.C = g.latent_w; w.ldc = s.Z;
+        w.M = s.H; w.N = s.Z; w.K = s.B;
+        w.accumulate = 1;
+        SVAE_TRY(sgemm(w, st));
+        if (dz) {
+            // dz (B,Z) = z_scale * S_s Wz
+            SgemmArgs x{};
+            x.A = S; x.sAm = 3L * p.Hp; x.sAk = 1;
+            x.B = dp.latent_w; x.sBk = s.Z; x.sBn = 1;
+            x.C = dz; x.ldc = s.Z;
+            x.M = s.B; x.N = s.Z; x.K = s.H;
+            x.alpha = z_scale;
+            SVAE_TRY(sgemm(x, st));
+        }
+    }
+    return SVAE_OK;
+}
+
+__global__ void finalize_stats_k(float* stats, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) stats[b * 3 + 2] = stats[b * 3 + 0] - stats[b * 3 + 1];
+}
+
+template <typename T>
+static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, const SvaeDecoderParams& dp,
+                     const SvaeEncoderParams& qp, const SvaeStepInputs& in, const SvaeStepOutputs& out,
+                     SvaeDecoderParams* gd, SvaeEncoderParams* gq, char* ws, cudaStream_t st) {
+    DecoderCtx<T> d{&s, &c, &p, ws, st};
+    const bool train = (gd != nullptr);
+    const float* x_enc = in.y_enc ? in.y_enc : in.y;
+    float* zo = d.f(p.zo);
+    SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st));
+    float* lat = out.latent ? out.latent : d.f(p.lat);
+    SVAE_TRY(latent_forward(s, c, zo, in.eps, in.theta_offset, lat, d.f(p.img), d.f(p.zs), out.stats, st));
+    SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
+    if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
+    for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
+        const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
+        SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, in.grid, nullptr, out.y_hat));
+        SVAE_TRY(likelihood(s, c, b0, nb, d.f(p.o), in.y, in.ctf, in.mask, out.stats, train ? d.f(p.g_o) : nullptr, st));
+        if (train) SVAE_TRY(decoder_chunk_backward<T>(d, dp, *gd, b0, nb, in.grid, nullptr, nullptr));
+    }
+    finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
+    SVAE_LAUNCH_CHECK();
+    if (train) {
+        SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
+                                         s.Z > 0 ? d.f(p.dz) : nullptr, st));
+        SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
+                                 in.eps, d.f(p.g_zo), st));
+        if (gq) SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
+                                               d.f(p.enc_scratch), st));
+    }
+    return SVAE_OK;
+}
+
+// module-level decoder (explicit coordinates)
+template <typename T>
+static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, const SvaeDecoderParams& dp,
+                        const float* x, const float* z, float* y_hat, const float* g_y, SvaeDecoderParams* gd,
+                        float* g_x, float* g_z, char* ws, cudaStream_t st);
+
+__global__ void scale_rows_k(const float* z, float* zs, long n, float sc) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) zs[i] = z[i] * sc;
+}
+// g_o = g_y * d(y_hat)/d(o) from the stored logits
+__global__ void logit_grad_k(const float* __restrict__ o, const float* __restrict__ g_y, float* __restrict__ g_o,
+                             long n, int C, int softplus) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sg = 1.f / (1.f + expf(-o[i]));
+    float dv = sg * (1.f - sg);
+    if (softplus && (i % C) == 0) dv *= 1.f / (1.f + expf(-sg));
+    g_o[i] = g_y[i] * dv;
+}
+
+template <typename T>
+static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, const SvaeDecoderParams& dp,
+                        const float* x, const float* z, float* y_hat, const float* g_y, SvaeDecoderParams* gd,
+                        float* g_x, float* g_z, char* ws, cudaStream_t st) {
+    DecoderCtx<T> d{&s, &c, &p, ws, st};
+    if (s.B == 0) return SVAE_OK;
+    if (s.Z > 0) {
+        scale_rows_k<<<ceil_div((long)s.B * s.Z, 256), 256, 0, st>>>(z, d.f(p.zs), (long)s.B * s.Z, 1.f);
+        SVAE_LAUNCH_CHECK();
+    }
+    SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
+    if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
+    for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
+        const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
+        SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, nullptr, x, y_hat));
+        if (gd) {
+            const long n = (long)nb * s.P * s.C;
+            logit_grad_k<<<ceil_div(n, 256), 256, 0, st>>>(d.f(p.o), g_y + (size_t)b0 * s.P * s.C, d.f(p.g_o), n, s.C,
+                                                           c.softplus);
+            SVAE_LAUNCH_CHECK();
+            SVAE_TRY(decoder_chunk_backward<T>(d, dp, *gd, b0, nb, nullptr, x, g_x));
+        }
+    }
+    if (gd) {
+        SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), nullptr, d.f(p.zs), 1.f, 1, g_z, st));
+    }
+    return SVAE_OK;
+}
+
+}  // namespace svae
+
+using namespace svae;
+
+extern "C" {
+
+int svae_version(void) { return 100; }
+
+int svae_last_error(char* buf, int n) {
+    if (buf && n > 0) {
+        strncpy(buf, g_err, (size_t)n - 1);
+        buf[n - 1] = '\0';
+    }
+    return (int)strlen(g_err);
+}
+
+int svae_device_sm_count(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SVAE_ECUDA;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SVAE_ECUDA;
+    return sms;
+}
+
+int svae_workspace_bytes(const SvaeShape* shape, const SvaeConfig* cfg, size_t* bytes) {
+    SVAE_REQUIRE(shape && cfg && bytes, SVAE_EINVAL, "null argument");
+    SVAE_TRY(validate(*shape, *cfg));
+    Plan p;
+    SVAE_TRY(make_plan(*shape, *cfg, p));
+    *bytes = p.total;
+    return SVAE_OK;
+}
+
+int svae_encoder_forward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params, const float* x,
+                         float* out, float* acts, void* stream) {
+    SVAE_REQUIRE(shape && params && x && out && acts, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(shape->Lq >= 1 && shape->Lq <= SVAE_MAX_LAYERS, SVAE_EINVAL, "bad encoder depth %d", shape->Lq);
+    if (shape->B == 0) return SVAE_OK;
+    return encoder_forward_impl(*shape, activation, *params, x, out, acts, (cudaStream_t)stream);
+}
+
+int svae_encoder_backward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params, const float* x,
+                          const float* acts, float* g_out, SvaeEncoderParams* grads, float* g_x, float* scratch,
+                          void* stream) {
+    SVAE_REQUIRE(shape && params && x && acts && g_out && grads && scratch, SVAE_EINVAL, "null argument");
+    if (shape->B == 0) return SVAE_OK;
+    return encoder_backward_impl(*shape, activation, *params, x, acts, g_out, *grads, g_x, scratch,
+                                 (cudaStream_t)stream);
+}
+
+static int decoder_shape_check(const SvaeShape& s, const SvaeConfig& c) {
+    SVAE_REQUIRE(s.B >= 0 && s.P > 0 && s.H > 0 && s.L >= 1 && s.L <= SVAE_MAX_LAYERS && s.C >= 1 && s.C <= 4,
+                 SVAE_EINVAL, "bad decoder shape");
+    SVAE_REQUIRE(c.activation >= 0 && c.activation <= 3, SVAE_EINVAL, "unknown activation %d", c.activation);
+    return SVAE_OK;
+}
+
+int svae_decoder_forward(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderParams* params,
+                         const float* x, const float* z, float* y_hat, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    SVAE_REQUIRE(shape && cfg && params && x && y_hat && workspace, SVAE_EINVAL, "null argument");
+    SVAE_TRY(decoder_shape_check(*shape, *cfg));
+    Plan p;
+    SVAE_TRY(make_plan(*shape, *cfg, p));
+    SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
+    if (cfg->precision == SVAE_PRECISION_FAST)
+        return decoder_impl<__nv_bfloat16>(*shape, *cfg, p, *params, x, z, y_hat, nullptr, nullptr, nullptr, nullptr,
+                                           (char*)workspace, (cudaStream_t)stream);
+    return decoder_impl<float>(*shape, *cfg, p, *params, x, z, y_hat, nullptr, nullptr, nullptr, nullptr,
+                               (char*)workspace, (cudaStream_t)stream);
+}
+
+int svae_decoder_backward(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderParams* params,
+                          const float* x, const float* z, const float* g_y, SvaeDecoderParams* grads, float* g_x,
+                          float* g_z, void* workspace, size_t workspace_bytes, void* stream) {
+    SVAE_REQUIRE(shape && cfg && params && x && g_y && grads && workspace, SVAE_EINVAL, "null argument");
+    SVAE_TRY(decoder_shape_check(*shape, *cfg));
+    Plan p;
+    SVAE_TRY(make_plan(*shape, *cfg, p));
+    SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
+    if (cfg->precision == SVAE_PRECISION_FAST)
+        return decoder_impl<__nv_bfloat16>(*shape, *cfg, p, *params, x, z, nullptr, g_y, grads, g_x, g_z,
+                                           (char*)workspace, (cudaStream_t)stream);
+    return decoder_impl<float>(*shape, *cfg, p, *params, x, z, nullptr, g_y, grads, g_x, g_z, (char*)workspace,
+                               (cudaStream_t)stream);
+}
+
+int svae_step(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderParams* dec,
+              const SvaeEncoderParams* enc, const SvaeStepInputs* in, const SvaeStepOutputs* out,
+              SvaeDecoderParams* dec_grads, SvaeEncoderParams* enc_grads, void* workspace, size_t workspace_bytes,
+              void* stream) {
+    SVAE_REQUIRE(shape && cfg && dec && enc && in && out && workspace, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(in->grid && in->y && in->eps && out->stats, SVAE_EINVAL, "grid, y, eps and stats are required");
+    SVAE_TRY(validate(*shape, *cfg));
+    SVAE_REQUIRE(shape->Lq >= 1 && shape->Lq <= SVAE_MAX_LAYERS, SVAE_EINVAL, "bad encoder depth %d", shape->Lq);
+    SVAE_REQUIRE((shape->k_ctf > 0) == (in->ctf != nullptr), SVAE_EINVAL, "k_ctf and the ctf pointer disagree");
+    SVAE_REQUIRE((dec_grads == nullptr) == (enc_grads == nullptr), SVAE_EINVAL,
+                 "pass both gradient structs or neither");
+    if (shape->B == 0) return SVAE_OK;
+    Plan p;
+    SVAE_TRY(make_plan(*shape, *cfg, p));
+    SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
+    if (cfg->precision == SVAE_PRECISION_FAST)
+        return step_impl<__nv_bfloat16>(*shape, *cfg, p, *dec, *enc, *in, *out, dec_grads, enc_grads,
+                                        (char*)workspace, (cudaStream_t)stream);
+    return step_impl<float>(*shape, *cfg, p, *dec, *enc, *in, *out, dec_grads, enc_grads, (char*)workspace,
+                            (cudaStream_t)stream);
+}
+
+int svae_adam_step(float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                   float eps, int t, int zero_grad, void* stream) {
+    SVAE_REQUIRE(param && grad && m && v, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(t >= 1, SVAE_EINVAL, "Adam step count starts at 1");
+    return adam(param, grad, m, v, n, lr, beta1, beta2, eps, t, zero_grad, (cudaStream_t)stream);
+}
+
+int svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
+                     void* stream) {
+    SVAE_REQUIRE(src && index && dst, SVAE_EINVAL, "null argument");
+    return gather_rows(src, index, dst, n_rows, row_len, (cudaStream_t)stream);
+}
+
+int svae_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
+                   const void* aux, int ldaux, int activation, void* out, int ldo, void* stream) {
+    SVAE_REQUIRE(A && W && out, SVAE_EINVAL, "null argument");
+    return tc_gemm(mode, M, N, K, A, lda, W, ldw, bias, N, aux, ldaux, activation, out, ldo, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Shared device/host helpers for libsvae_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/svae_b200.h"
+
+namespace svae {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SVAE_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return svae::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define SVAE_LAUNCH_CHECK() SVAE_CUDA(cudaPeekAtLastError())
+#define SVAE_TRY(call)                                                         \
+    do {                                                                       \
+        int r__ = (call);                                                      \
+        if (r__ != SVAE_OK) return r__;                                        \
+    } while (0)
+#define SVAE_REQUIRE(cond, code, ...)                                          \
+    do {                                                                       \
+        if (!(cond)) { svae::set_error(__VA_ARGS__); return (code); }          \
+    } while (0)
+
+__host__ __device__ static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// ---- activations ----------------------------------------------------------------------------
+// Forward value and derivative expressed through the OUTPUT h = act(a), which is what the
+// workspace keeps (tanh' = 1-h^2, sigmoid' = h(1-h); for (leaky)relu sign(h) == sign(a)).
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool FAST>
+__device__ __forceinline__ float act_apply(int act, float a) {
+    switch (act) {
+        case SVAE_ACT_TANH:      return FAST ? tanh_fast(a) : tanhf(a);
+        case SVAE_ACT_LEAKYRELU: return a > 0.f ? a : 0.01f * a;
+        case SVAE_ACT_RELU:      return a > 0.f ? a : 0.f;
+        default:                 return 1.f / (1.f + expf(-a));
+    }
+}
+
+__device__ __forceinline__ float act_deriv_from_out(int act, float h) {
+    switch (act) {
+        case SVAE_ACT_TANH:      return 1.f - h * h;
+        case SVAE_ACT_LEAKYRELU: return h > 0.f ? 1.f : 0.01f;
+        case SVAE_ACT_RELU:      return h > 0.f ? 1.f : 0.f;
+        default:                 return h * (1.f - h);
+    }
+}
+
+// ---- storage type of the (rows x Hp) activation matrices: float (parity) or bf16 (fast) -------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- fp32 SIMT GEMM (sgemm.cu) ---------------------------------------------------------------
+// C[m,n] (op)= alpha * sum_k A(m,k) * B(k,n)  with arbitrary element strides, then the epilogue
+//   v += bias[n];  v = act(v);  v *= act'(dsrc[m*ld_dsrc + n])
+// accumulate = 1 adds into C with atomics (required when split_k > 1).
+struct SgemmArgs {
+    const float* A; long sAm, sAk;
+    const float* B; long sBk, sBn;
+    float* C; long ldc;
+    int M, N, K;
+    const float* bias = nullptr;
+    int act = -1;
+    const float* dsrc = nullptr; long ld_dsrc = 0; int dact = -1;
+    int accumulate = 0;
+    int split_k = 1;
+    float alpha = 1.f;
+};
+int sgemm(const SgemmArgs& a, cudaStream_t st);
+
+// ---- bf16 tcgen05 GEMMs (tc_gemm.cu) -----------------------------------------------------------
+int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
+            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st);
+
+}  // namespace svae

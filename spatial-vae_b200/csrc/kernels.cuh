@@ -1,0 +1,71 @@
+// Launch wrappers of the SIMT kernels of the step (step_kernels.cu).  T is the storage type of
+// the (rows x Hp) activation matrices: float (PARITY) or __nv_bfloat16 (FAST).
+#pragma once
+#include "common.cuh"
+
+namespace svae {
+
+// Reparameterisation + KL (train_mnist.py:33-39,62-63,84-86).  One thread per image.
+//   zo (B,2I) = [mu | logstd]; writes lat (B,I), img (B,4) = cos,sin,dx0,dx1, zs (B,Z) scaled z,
+//   stats[b*3+1] = kl_b.
+int latent_forward(const SvaeShape& s, const SvaeConfig& c, const float* zo, const float* eps,
+                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st);
+
+// hz[b, n] = coord_b[n] for all b when Z == 0 (otherwise an sgemm with bias does it)
+int fill_rows(float* dst, const float* row, int rows, int n, int ld, cudaStream_t st);
+
+// First layer (models.py:104-124 + layers[0]): h0[r,n] = act(Wc[n,0]*x0' + Wc[n,1]*x1' + hz[b,n]).
+// Coordinates come either from (grid, img) -> R(theta)*grid + dx, or from explicit x (B,P,2).
+template <typename T>
+int layer0_forward(const SvaeShape& s, int act, int b0, int nb, const float* coord_w, const float* hz,
+                   const float* grid, const float* img, const float* x_explicit, int H, int Hp, T* h0,
+                   cudaStream_t st);
+
+// Output layer + sigmoid (+softplus ch0) (models.py:84-85,129-130): warp-shuffle dot per row.
+// Writes logits o (rows,C) and, if non-NULL, y_hat (rows,C).
+template <typename T>
+int out_forward(const T* h, int rows, int H, int Hp, int C, const float* out_w, const float* out_b, int softplus,
+                float* o, float* y_hat, cudaStream_t st);
+
+// Likelihood per image (train_mnist.py:80-81, train_particles.py:102-139, train_galaxy.py:118-119):
+// reads logits o (nb,P,C), targets, optional CTF kernels and mask; writes stats[b*3+0] = logp_b and
+// g_o (nb,P,C) = grad_scale * d(-logp_b)/do.
+int likelihood(const SvaeShape& s, const SvaeConfig& c, int b0, int nb, const float* o, const float* y,
+               const float* ctf, const uint8_t* mask, float* stats, float* g_o, cudaStream_t st);
+
+// Output-layer backward: delta[r,n] = (sum_c g_o[r,c] Wo[c,n]) * act'(h[r,n]); accumulates
+// dWo += g_o^T h, dbo += colsum(g_o), db_last += colsum(delta) (db_last may be NULL).
+template <typename T>
+int out_backward(const T* h, const float* g_o, int rows, int H, int Hp, int C, int act, const float* out_w,
+                 T* delta, float* d_out_w, float* d_out_b, float* d_b_last, cudaStream_t st);
+
+// colsum: dst[n] += sum_r src[r,n]   (hidden-layer bias gradients)
+template <typename T>
+int col_sum(const T* src, int rows, int H, int Hp, float* dst, cudaStream_t st);
+
+// Per-image column reductions of delta0: S[b,0,n] = sum_p d, S[b,1,n] = sum_p c0 d,
+// S[b,2,n] = sum_p c1 d with (c0,c1) the UNtransformed grid coordinate (or explicit x[b,p,:]).
+template <typename T>
+int image_col_reduce(const T* delta0, int b0, int nb, int P, int Hp, const float* grid, const float* x_explicit,
+                     float* S, cudaStream_t st);
+
+// Row gradients w.r.t. explicit coordinates: g_x[r,k] = sum_n delta0[r,n] Wc[n,k]
+template <typename T>
+int coord_row_grad(const T* delta0, int rows, int H, int Hp, const float* coord_w, float* g_x, cudaStream_t st);
+
+// dWc, dbc from S and the per-image transform; explicit != 0: S already holds x-moments.
+int coord_param_grad(const float* S, const float* img, int B, int H, int Hp, int explicit_x, float* d_coord_w,
+                     float* d_coord_b, cudaStream_t st);
+
+// Per-image latent gradient -> encoder head gradient g_zo (B,2I) (SURVEY 7.3 last line).
+int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
+                    const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
+                    cudaStream_t st);
+
+int adam(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, int t,
+         int zero_grad, cudaStream_t st);
+int gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int64_t row_len, cudaStream_t st);
+// dst (rows_p x cols_p, bf16, zero padded) = src (rows x cols fp32)
+int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p, cudaStream_t st);
+
+}  // namespace svae

@@ -1,0 +1,680 @@
+// SIMT kernels of the spatial-VAE step: everything that is not a dense HxH contraction.
+// Reference line numbers are relative to the reference checkout (see include/svae_b200.h).
+#include <type_traits>
+
+#include "kernels.cuh"
+
+namespace svae {
+
+// ------------------------------------------------------------------------------------------------
+// small load/store helpers for pairs of adjacent columns of an activation row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load2(const float* p, float& a, float& b) {
+    float2 v = *reinterpret_cast<const float2*>(p);
+    a = v.x; b = v.y;
+}
+__device__ __forceinline__ void load2(const __nv_bfloat16* p, float& a, float& b) {
+    __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+    a = __low2float(v); b = __high2float(v);
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    if (w == 0) t = warp_sum(t);
+    return t;  // valid in warp 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// reparameterisation + KL   (train_mnist.py:33-39,62-63,84-86; particles :85-86,99)
+// ------------------------------------------------------------------------------------------------
+__global__ void latent_forward_k(SvaeShape s, SvaeConfig c, const float* __restrict__ zo,
+                                 const float* __restrict__ eps, const float* __restrict__ toff,
+                                 float* __restrict__ lat, float* __restrict__ img, float* __restrict__ zs,
+                                 float* __restrict__ stats) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    const int I = s.I;
+    const float* mu = zo + (long)b * 2 * I;
+    const float* ls = mu + I;
+    const int rot = c.rotate ? 1 : 0;
+    const int zcol = rot + (c.translate ? 2 : 0);
+    float kl = 0.f, cs = 1.f, sn = 0.f, dx0 = 0.f, dx1 = 0.f;
+    for (int i = 0; i < I; ++i) {
+        const float m = mu[i], l = ls[i];
+        const float sd = expf(l);
+        const float v = sd * eps[(long)b * I + i] + m;
+        if (lat) lat[(long)b * I + i] = v;
+        if (rot && i == 0) {
+            const float th = v + (toff ? toff[b] : 0.f);
+            cs = cosf(th);
+            sn = sinf(th);
+            const float sp = c.theta_prior;
+            const float num = c.theta_kl_mean ? (sd * sd + m * m) : (sd * sd);
+            kl += -l + logf(sp) + num / 2.f / (sp * sp) - 0.5f;
+        } else {
+            kl += -l + 0.5f * sd * sd + 0.5f * m * m - 0.5f;
+            if (i < zcol) {
+                if (i - rot == 0) dx0 = v * c.dx_scale; else dx1 = v * c.dx_scale;
+            } else {
+                zs[(long)b * s.Z + (i - zcol)] = v * c.z_scale;
+            }
+        }
+    }
+    img[b * 4 + 0] = cs; img[b * 4 + 1] = sn; img[b * 4 + 2] = dx0; img[b * 4 + 3] = dx1;
+    stats[b * 3 + 1] = kl;
+}
+
+int latent_forward(const SvaeShape& s, const SvaeConfig& c, const float* zo, const float* eps,
+                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st) {
+    latent_forward_k<<<ceil_div(s.B, 128), 128, 0, st>>>(s, c, zo, eps, theta_offset, lat, img, zs, stats);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+__global__ void fill_rows_k(float* dst, const float* row, int rows, int n, int ld) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows * n) return;
+    int r = (int)(i / n), c = (int)(i % n);
+    dst[(long)r * ld + c] = row[c];
+}
+int fill_rows(float* dst, const float* row, int rows, int n, int ld, cudaStream_t st) {
+    fill_rows_k<<<ceil_div((long)rows * n, 256), 256, 0, st>>>(dst, row, rows, n, ld);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer: rotate/translate the grid in registers, K=2 coordinate layer + per-image z projection
+// (train_mnist.py:50-59,70-74; models.py:104-124 and layers[0])
+// ------------------------------------------------------------------------------------------------
+constexpr int L0_ROWS = 64;
+
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) layer0_k(int P, int act, int b0, const float* __restrict__ coord_w,
+                                                const float* __restrict__ hz, const float* __restrict__ grid,
+                                                const float* __restrict__ img, const float* __restrict__ xe,
+                                                int H, int Hp, T* __restrict__ h0) {
+    __shared__ float sx[L0_ROWS][2];
+    const int bl = blockIdx.y;          // image within the chunk
+    const int b = b0 + bl;              // image within the call
+    const int p0 = blockIdx.x * L0_ROWS;
+    const int nrows = min(L0_ROWS, P - p0);
+    if (threadIdx.x < nrows) {
+        const int p = p0 + threadIdx.x;
+        float x0, x1;
+        if (xe) {
+            x0 = xe[((long)b * P + p) * 2 + 0];
+            x1 = xe[((long)b * P + p) * 2 + 1];
+        } else {
+            const float g0 = grid[p * 2 + 0], g1 = grid[p * 2 + 1];
+            const float cs = img[b * 4 + 0], sn = img[b * 4 + 1];
+            x0 = g0 * cs - g1 * sn + img[b * 4 + 2];
+            x1 = g0 * sn + g1 * cs + img[b * 4 + 3];
+        }
+        sx[threadIdx.x][0] = x0;
+        sx[threadIdx.x][1] = x1;
+    }
+    __syncthreads();
+    T* out = h0 + ((long)bl * P + p0) * Hp;
+    for (int n = threadIdx.x; n < Hp; n += blockDim.x) {
+        float w0 = 0.f, w1 = 0.f, hb = 0.f;
+        if (n < H) {
+            w0 = coord_w[n * 2 + 0];
+            w1 = coord_w[n * 2 + 1];
+            hb = hz[(long)b * Hp + n];
+        }
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) {
+            const float a = fmaf(w0, sx[r][0], fmaf(w1, sx[r][1], hb));
+            out[(long)r * Hp + n] = from_f32<T>(act_apply<FAST>(act, a));
+        }
+    }
+}
+
+template <typename T>
+int layer0_forward(const SvaeShape& s, int act, int b0, int nb, const float* coord_w, const float* hz,
+                   const float* grid, const float* img, const float* x_explicit, int H, int Hp, T* h0,
+                   cudaStream_t st) {
+    dim3 g(ceil_div(s.P, L0_ROWS), nb);
+    constexpr bool FAST = !std::is_same<T, float>::value;
+    layer0_k<T, FAST><<<g, 256, 0, st>>>(s.P, act, b0, coord_w, hz, grid, img, x_explicit, H, Hp, h0);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int layer0_forward<float>(const SvaeShape&, int, int, int, const float*, const float*, const float*,
+                                   const float*, const float*, int, int, float*, cudaStream_t);
+template int layer0_forward<__nv_bfloat16>(const SvaeShape&, int, int, int, const float*, const float*,
+                                           const float*, const float*, const float*, int, int, __nv_bfloat16*,
+                                           cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// output layer: warp-shuffle dot product per row, sigmoid (+softplus)   (models.py:84-85,129-130)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// value of output element with channel ch and its derivative w.r.t. the logit
+__device__ __forceinline__ void post_output(float o, int ch, int softplus, float& v, float& dv) {
+    const float sg = sigmoidf_(o);
+    if (softplus && ch == 0) {
+        v = log1pf(expf(sg));
+        dv = sigmoidf_(sg) * sg * (1.f - sg);
+    } else {
+        v = sg;
+        dv = sg * (1.f - sg);
+    }
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) out_forward_k(const T* __restrict__ h, int rows, int H, int Hp,
+                                                     const float* __restrict__ out_w,
+                                                     const float* __restrict__ out_b, int softplus,
+                                                     float* __restrict__ o, float* __restrict__ y_hat) {
+    extern __shared__ float sw[];  // C x Hp, zero padded
+    for (int i = threadIdx.x; i < C * Hp; i += blockDim.x) {
+        const int c = i / Hp, n = i % Hp;
+        sw[i] = (n < H) ? out_w[c * H + n] : 0.f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long r = (long)blockIdx.x * 8 + warp; r < rows; r += (long)gridDim.x * 8) {
+        const T* hr = h + r * Hp;
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int n = lane * 2; n < Hp; n += 64) {
+            float a, b;
+            load2(hr + n, a, b);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(a, sw[c * Hp + n], fmaf(b, sw[c * Hp + n + 1], acc[c]));
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
+        if (lane < C) {
+            float val = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) if (lane == c) val = acc[c];
+            val += out_b[lane];
+            o[r * C + lane] = val;
+            if (y_hat) {
+                float v, dv;
+                post_output(val, lane, softplus, v, dv);
+                y_hat[r * C + lane] = v;
+            }
+        }
+    }
+}
+
+template <typename T>
+int out_forward(const T* h, int rows, int H, int Hp, int C, const float* out_w, const float* out_b, int softplus,
+                float* o, float* y_hat, cudaStream_t st) {
+    const int blocks = min(ceil_div(rows, 8), 148 * 8);
+    const size_t smem = (size_t)C * Hp * sizeof(float);
+    switch (C) {
+        case 1: out_forward_k<T, 1><<<blocks, 256, smem, st>>>(h, rows, H, Hp, out_w, out_b, softplus, o, y_hat); break;
+        case 2: out_forward_k<T, 2><<<blocks, 256, smem, st>>>(h, rows, H, Hp, out_w, out_b, softplus, o, y_hat); break;
+        case 3: out_forward_k<T, 3><<<blocks, 256, smem, st>>>(h, rows, H, Hp, out_w, out_b, softplus, o, y_hat); break;
+        case 4: out_forward_k<T, 4><<<blocks, 256, smem, st>>>(h, rows, H, Hp, out_w, out_b, softplus, o, y_hat); break;
+        default: set_error("n_out=%d not supported (1..4)", C); return SVAE_EINVAL;
+    }
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int out_forward<float>(const float*, int, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
+template int out_forward<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// likelihood, one block per image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) likelihood_k(SvaeShape s, SvaeConfig c, int b0, const float* __restrict__ o,
+                                                    const float* __restrict__ y, const float* __restrict__ ctf,
+                                                    const uint8_t* __restrict__ mask, float* __restrict__ stats,
+                                                    float* __restrict__ g_o) {
+    extern __shared__ float sm[];
+    __shared__ float red[8];
+    const int bl = blockIdx.x, b = b0 + bl;
+    const int P = s.P, C = s.C;
+    const long E = (long)P * C;
+    const float* ob = o + (long)bl * E;
+    float* gb = g_o ? g_o + (long)bl * E : nullptr;
+    const float gs = c.grad_scale;
+    float ll = 0.f;
+
+    if (c.likelihood == SVAE_LIK_BERNOULLI) {
+        // -BCE with both logs clamped at -100, backward divides by max(p(1-p),1e-12)
+        // (train_mnist.py:80-81; ATen binary_cross_entropy)
+        const float* yb = y + (long)b * E;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            float v, dv;
+            post_output(ob[e], e % C, c.softplus, v, dv);
+            const float t = yb[e];
+            const float lp = fmaxf(logf(v), -100.f), lq = fmaxf(log1pf(-v), -100.f);
+            ll += t * lp + (1.f - t) * lq;
+            if (gb) gb[e] = gs * (v - t) / fmaxf(v * (1.f - v), 1e-12f) * dv;
+        }
+    } else if (c.likelihood == SVAE_LIK_GAUSS_FITNOISE) {
+        // y_params.view(B,-1): first P flat entries are the mean, last P the log-variance
+        // (train_particles.py:102-110,136-137): the interleave quirk of SURVEY Appendix A #2.
+        const float* yb = y + (long)b * P;
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            float mu, dmu, lv, dlv;
+            post_output(ob[j], j % C, c.softplus, mu, dmu);
+            post_output(ob[P + j], (P + j) % C, c.softplus, lv, dlv);
+            const float m = mask ? (mask[j] ? 1.f : 0.f) : 1.f;
+            const float r = mu - yb[j];
+            const float iv = expf(-lv);
+            ll -= 0.5f * m * (r * r * iv + lv);
+            if (gb) {
+                gb[j] = gs * m * r * iv * dmu;
+                gb[P + j] = gs * 0.5f * m * (1.f - r * r * iv) * dlv;
+            }
+        }
+    } else if (ctf == nullptr) {
+        // unit-variance Gaussian (train_particles.py:138-139)
+        const float* yb = y + (long)b * P;
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            float mu, dmu;
+            post_output(ob[j], 0, c.softplus, mu, dmu);
+            const float m = mask ? (mask[j] ? 1.f : 0.f) : 1.f;
+            const float r = m * (mu - yb[j]);
+            ll -= 0.5f * r * r;
+            if (gb) gb[j] = gs * r * dmu;
+        }
+    } else {
+        // CTF: per-image cross-correlation with its own k x k kernel, zero padding k/2
+        // (train_particles.py:112-119), then the unit-variance Gaussian on the filtered mean.
+        const int nr = s.n_rows, nc = s.n_cols, k = s.k_ctf, pad = k / 2;
+        float* smu = sm;             // P
+        float* sres = sm + P;        // P
+        float* sk = sm + 2 * P;      // k*k
+        const float* yb = y + (long)b * P;
+        const float* kb = ctf + (long)b * k * k;
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            float mu, dmu;
+            post_output(ob[j], 0, c.softplus, mu, dmu);
+            smu[j] = mu;
+        }
+        for (int j = threadIdx.x; j < k * k; j += blockDim.x) sk[j] = kb[j];
+        __syncthreads();
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            const int i0 = j / nc, j0 = j % nc;
+            float acc = 0.f;
+            for (int a = 0; a < k; ++a) {
+                const int ii = i0 + a - pad;
+                if (ii < 0 || ii >= nr) continue;
+                const int blo = max(0, pad - j0), bhi = min(k, nc + pad - j0);
+                const float* mrow = smu + ii * nc + (j0 - pad);
+                const float* krow = sk + a * k;
+                for (int bb = blo; bb < bhi; ++bb) acc = fmaf(mrow[bb], krow[bb], acc);
+            }
+            const float m = mask ? (mask[j] ? 1.f : 0.f) : 1.f;
+            const float r = m * (acc - yb[j]);
+            sres[j] = r;
+            ll -= 0.5f * r * r;
+        }
+        __syncthreads();
+        if (gb) {
+            for (int j = threadIdx.x; j < P; j += blockDim.x) {
+                const int u = j / nc, v = j % nc;
+                float acc = 0.f;
+                for (int a = 0; a < k; ++a) {
+                    const int ii = u - a + pad;
+                    if (ii < 0 || ii >= nr) continue;
+                    // jj = v - bb + pad in [0, nc)
+                    const int blo = max(0, v + pad - nc + 1), bhi = min(k, v + pad + 1);
+                    const float* rrow = sres + ii * nc + (v + pad);
+                    const float* krow = sk + a * k;
+                    for (int bb = blo; bb < bhi; ++bb) acc = fmaf(rrow[-bb], krow[bb], acc);
+                }
+                float mu, dmu;
+                post_output(ob[j], 0, c.softplus, mu, dmu);
+                gb[j] = gs * acc * dmu;
+            }
+        }
+    }
+    const float tot = block_sum_256(ll, red);
+    if (threadIdx.x == 0) stats[b * 3 + 0] = tot;
+}
+
+int likelihood(const SvaeShape& s, const SvaeConfig& c, int b0, int nb, const float* o, const float* y,
+               const float* ctf, const uint8_t* mask, float* stats, float* g_o, cudaStream_t st) {
+    size_t smem = 0;
+    if (c.likelihood == SVAE_LIK_GAUSS && ctf != nullptr) {
+        smem = ((size_t)2 * s.P + (size_t)s.k_ctf * s.k_ctf) * sizeof(float);
+        if (smem > 48 * 1024) {
+            SVAE_CUDA(cudaFuncSetAttribute(likelihood_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
+    likelihood_k<<<nb, 256, smem, st>>>(s, c, b0, o, y, ctf, mask, stats, g_o);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// output-layer backward: thread <-> column pair, loop over rows; no cross-thread reductions
+// ------------------------------------------------------------------------------------------------
+constexpr int OB_ROWS = 128;
+constexpr int OB_MAXPAIRS = 4;   // Hp <= 2048
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) out_backward_k(const T* __restrict__ h, const float* __restrict__ g_o,
+                                                      int rows, int H, int Hp, int act,
+                                                      const float* __restrict__ out_w, T* __restrict__ delta,
+                                                      float* __restrict__ d_out_w, float* __restrict__ d_out_b,
+                                                      float* __restrict__ d_b_last) {
+    __shared__ float sg[OB_ROWS][C];
+    const long r0 = (long)blockIdx.x * OB_ROWS;
+    const int nrows = (int)min((long)OB_ROWS, rows - r0);
+    for (int i = threadIdx.x; i < nrows * C; i += blockDim.x) sg[i / C][i % C] = g_o[r0 * C + i];
+    __syncthreads();
+    const int npairs = Hp / 2;
+    float w[OB_MAXPAIRS][2][C], aw[OB_MAXPAIRS][2][C], ab[OB_MAXPAIRS][2];
+#pragma unroll
+    for (int q = 0; q < OB_MAXPAIRS; ++q) {
+        const int n = (threadIdx.x + q * 256) * 2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            ab[q][e] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                aw[q][e][c] = 0.f;
+                w[q][e][c] = (n + e < H) ? out_w[c * H + n + e] : 0.f;
+            }
+        }
+    }
+    for (int r = 0; r < nrows; ++r) {
+        float g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = sg[r][c];
+#pragma unroll
+        for (int q = 0; q < OB_MAXPAIRS; ++q) {
+            const int pr = threadIdx.x + q * 256;
+            if (pr < npairs) {
+                float hv[2];
+                load2(h + (r0 + r) * Hp + pr * 2, hv[0], hv[1]);
+                float dv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        t = fmaf(g[c], w[q][e][c], t);
+                        aw[q][e][c] = fmaf(g[c], hv[e], aw[q][e][c]);
+                    }
+                    dv[e] = t * act_deriv_from_out(act, hv[e]);
+                    ab[q][e] += dv[e];
+                }
+                store2(delta + (r0 + r) * Hp + pr * 2, dv[0], dv[1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < OB_MAXPAIRS; ++q) {
+        const int n = (threadIdx.x + q * 256) * 2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (n + e < H) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) atomicAdd(d_out_w + c * H + n + e, aw[q][e][c]);
+                if (d_b_last) atomicAdd(d_b_last + n + e, ab[q][e]);
+            }
+        }
+    }
+    if (threadIdx.x < C) {
+        float t = 0.f;
+        for (int r = 0; r < nrows; ++r) t += sg[r][threadIdx.x];
+        atomicAdd(d_out_b + threadIdx.x, t);
+    }
+}
+
+template <typename T>
+int out_backward(const T* h, const float* g_o, int rows, int H, int Hp, int C, int act, const float* out_w,
+                 T* delta, float* d_out_w, float* d_out_b, float* d_b_last, cudaStream_t st) {
+    SVAE_REQUIRE(Hp <= 2 * 256 * OB_MAXPAIRS, SVAE_EINVAL, "hidden width %d too large", Hp);
+    const int blocks = ceil_div(rows, OB_ROWS);
+    switch (C) {
+        case 1: out_backward_k<T, 1><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+        case 2: out_backward_k<T, 2><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+        case 3: out_backward_k<T, 3><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+        case 4: out_backward_k<T, 4><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+        default: set_error("n_out=%d not supported (1..4)", C); return SVAE_EINVAL;
+    }
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int out_backward<float>(const float*, const float*, int, int, int, int, int, const float*, float*, float*, float*, float*, cudaStream_t);
+template int out_backward<__nv_bfloat16>(const __nv_bfloat16*, const float*, int, int, int, int, int, const float*, __nv_bfloat16*, float*, float*, float*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients) and per-image coordinate moments of delta0
+// ------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(256) col_sum_k(const T* __restrict__ src, int rows, int H, int Hp,
+                                                 float* __restrict__ dst) {
+    const long r0 = (long)blockIdx.x * CS_ROWS;
+    const int nrows = (int)min((long)CS_ROWS, rows - r0);
+    for (int pr = threadIdx.x; pr < Hp / 2; pr += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < nrows; ++r) {
+            float x, y;
+            load2(src + (r0 + r) * Hp + pr * 2, x, y);
+            a0 += x; a1 += y;
+        }
+        if (pr * 2 < H) atomicAdd(dst + pr * 2, a0);
+        if (pr * 2 + 1 < H) atomicAdd(dst + pr * 2 + 1, a1);
+    }
+}
+template <typename T>
+int col_sum(const T* src, int rows, int H, int Hp, float* dst, cudaStream_t st) {
+    col_sum_k<T><<<ceil_div(rows, CS_ROWS), 256, 0, st>>>(src, rows, H, Hp, dst);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int col_sum<float>(const float*, int, int, int, float*, cudaStream_t);
+template int col_sum<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, float*, cudaStream_t);
+
+template <typename T>
+__global__ void __launch_bounds__(256) image_col_reduce_k(const T* __restrict__ d0, int b0, int P, int Hp,
+                                                          const float* __restrict__ grid,
+                                                          const float* __restrict__ xe, float* __restrict__ S) {
+    const int bl = blockIdx.x, b = b0 + bl;
+    const float* coords = xe ? xe + (long)b * P * 2 : grid;
+    const T* base = d0 + (long)bl * P * Hp;
+    float* Sb = S + (long)b * 3 * Hp;
+    for (int pr = threadIdx.x + blockIdx.y * blockDim.x; pr < Hp / 2; pr += blockDim.x * gridDim.y) {
+        float s0 = 0.f, s1 = 0.f, m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
+        for (int p = 0; p < P; ++p) {
+            float x, y;
+            load2(base + (long)p * Hp + pr * 2, x, y);
+            const float c0 = __ldg(coords + p * 2), c1 = __ldg(coords + p * 2 + 1);
+            s0 += x; s1 += y;
+            m00 = fmaf(c0, x, m00); m01 = fmaf(c0, y, m01);
+            m10 = fmaf(c1, x, m10); m11 = fmaf(c1, y, m11);
+        }
+        Sb[pr * 2] = s0; Sb[pr * 2 + 1] = s1;
+        Sb[Hp + pr * 2] = m00; Sb[Hp + pr * 2 + 1] = m01;
+        Sb[2 * Hp + pr * 2] = m10; Sb[2 * Hp + pr * 2 + 1] = m11;
+    }
+}
+template <typename T>
+int image_col_reduce(const T* delta0, int b0, int nb, int P, int Hp, const float* grid, const float* x_explicit,
+                     float* S, cudaStream_t st) {
+    dim3 g(nb, ceil_div(Hp / 2, 256));
+    image_col_reduce_k<T><<<g, 256, 0, st>>>(delta0, b0, P, Hp, grid, x_explicit, S);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int image_col_reduce<float>(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+template int image_col_reduce<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+
+template <typename T>
+__global__ void __launch_bounds__(256) coord_row_grad_k(const T* __restrict__ d0, int rows, int H, int Hp,
+                                                        const float* __restrict__ coord_w, float* __restrict__ gx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long r = (long)blockIdx.x * 8 + warp; r < rows; r += (long)gridDim.x * 8) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int n = lane * 2; n < Hp; n += 64) {
+            float x, y;
+            load2(d0 + r * Hp + n, x, y);
+            if (n < H) { a0 = fmaf(x, __ldg(coord_w + n * 2), a0); a1 = fmaf(x, __ldg(coord_w + n * 2 + 1), a1); }
+            if (n + 1 < H) { a0 = fmaf(y, __ldg(coord_w + n * 2 + 2), a0); a1 = fmaf(y, __ldg(coord_w + n * 2 + 3), a1); }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1);
+        if (lane == 0) { gx[r * 2] = a0; gx[r * 2 + 1] = a1; }
+    }
+}
+template <typename T>
+int coord_row_grad(const T* delta0, int rows, int H, int Hp, const float* coord_w, float* g_x, cudaStream_t st) {
+    coord_row_grad_k<T><<<min(ceil_div(rows, 8), 148 * 8), 256, 0, st>>>(delta0, rows, H, Hp, coord_w, g_x);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int coord_row_grad<float>(const float*, int, int, int, const float*, float*, cudaStream_t);
+template int coord_row_grad<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, const float*, float*, cudaStream_t);
+
+// dWc / dbc from the per-image sums
+__global__ void coord_param_grad_k(const float* __restrict__ S, const float* __restrict__ img, int B, int H, int Hp,
+                                   int explicit_x, float* __restrict__ dw, float* __restrict__ db) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= H) return;
+    const int per = ceil_div(B, gridDim.y);
+    const int bs = blockIdx.y * per, be = min(B, bs + per);
+    float a0 = 0.f, a1 = 0.f, ab = 0.f;
+    for (int b = bs; b < be; ++b) {
+        const float* Sb = S + (long)b * 3 * Hp;
+        const float s = Sb[n], m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
+        ab += s;
+        if (explicit_x) { a0 += m0; a1 += m1; }
+        else {
+            const float cs = img[b * 4], sn = img[b * 4 + 1], dx0 = img[b * 4 + 2], dx1 = img[b * 4 + 3];
+            a0 += cs * m0 - sn * m1 + dx0 * s;
+            a1 += sn * m0 + cs * m1 + dx1 * s;
+        }
+    }
+    atomicAdd(dw + n * 2, a0);
+    atomicAdd(dw + n * 2 + 1, a1);
+    atomicAdd(db + n, ab);
+}
+int coord_param_grad(const float* S, const float* img, int B, int H, int Hp, int explicit_x, float* d_coord_w,
+                     float* d_coord_b, cudaStream_t st) {
+    dim3 g(ceil_div(H, 128), min(ceil_div(B, 32), 64));
+    coord_param_grad_k<<<g, 128, 0, st>>>(S, img, B, H, Hp, explicit_x, d_coord_w, d_coord_b);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// per-image d(theta), d(dx) and the chain into the encoder head; one warp per image
+__global__ void __launch_bounds__(256) latent_backward_k(SvaeShape s, SvaeConfig c, const float* __restrict__ S,
+                                                         int Hp, const float* __restrict__ img,
+                                                         const float* __restrict__ coord_w,
+                                                         const float* __restrict__ dz, const float* __restrict__ zo,
+                                                         const float* __restrict__ eps, float* __restrict__ g_zo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= s.B) return;
+    const float* Sb = S + (long)b * 3 * Hp;
+    const float cs = img[b * 4], sn = img[b * 4 + 1];
+    float dth = 0.f, d0 = 0.f, d1 = 0.f;
+    for (int n = lane; n < s.H; n += 32) {
+        const float w0 = coord_w[n * 2], w1 = coord_w[n * 2 + 1];
+        const float sv = Sb[n], m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
+        dth = fmaf(w0, -sn * m0 - cs * m1, fmaf(w1, cs * m0 - sn * m1, dth));
+        d0 = fmaf(w0, sv, d0);
+        d1 = fmaf(w1, sv, d1);
+    }
+    dth = warp_sum(dth); d0 = warp_sum(d0); d1 = warp_sum(d1);
+    const int I = s.I, rot = c.rotate ? 1 : 0, zcol = rot + (c.translate ? 2 : 0);
+    const float gs = c.grad_scale;
+    for (int i = lane; i < I; i += 32) {
+        const float mu = zo[(long)b * 2 * I + i], ls = zo[(long)b * 2 * I + I + i];
+        const float sd = expf(ls);
+        float gl, kmu, kls;
+        if (rot && i == 0) {
+            gl = dth;
+            const float sp2 = c.theta_prior * c.theta_prior;
+            kmu = c.theta_kl_mean ? mu / sp2 : 0.f;
+            kls = -1.f + sd * sd / sp2;
+        } else {
+            if (i < zcol) gl = ((i - rot) == 0 ? d0 : d1) * c.dx_scale;
+            else gl = dz ? dz[(long)b * s.Z + (i - zcol)] : 0.f;
+            kmu = mu;
+            kls = -1.f + sd * sd;
+        }
+        g_zo[(long)b * 2 * I + i] = gl + gs * kmu;
+        g_zo[(long)b * 2 * I + I + i] = gl * sd * eps[(long)b * I + i] + gs * kls;
+    }
+}
+int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
+                    const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
+                    cudaStream_t st) {
+    latent_backward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, S, Hp, img, coord_w, dz, zo, eps, g_zo);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, train_mnist.py:389-392,149-150), gather, fp32 -> padded bf16
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       size_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, int zero_grad) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+int adam(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, int t,
+         int zero_grad, cudaStream_t st) {
+    if (n == 0) return SVAE_OK;
+    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+    const int blocks = (int)min((size_t)148 * 16, (n + 255) / 256);
+    adam_k<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), zero_grad);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+__global__ void gather_rows_k(const float* __restrict__ src, const int64_t* __restrict__ idx, float* __restrict__ dst,
+                              int64_t n_rows, int64_t row_len) {
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const float* s = src + idx[r] * row_len;
+        float* d = dst + r * row_len;
+        for (int64_t i = threadIdx.x; i < row_len; i += blockDim.x) d[i] = __ldg(s + i);
+    }
+}
+int gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int64_t row_len, cudaStream_t st) {
+    if (n_rows == 0) return SVAE_OK;
+    gather_rows_k<<<(int)min((int64_t)148 * 8, n_rows), 256, 0, st>>>(src, idx, dst, n_rows, row_len);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+__global__ void to_bf16_padded_k(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
+                                 int rows_p, int cols_p) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows_p * cols_p) return;
+    const int r = (int)(i / cols_p), c = (int)(i % cols_p);
+    dst[i] = __float2bfloat16_rn((r < rows && c < cols) ? src[(long)r * cols + c] : 0.f);
+}
+int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p, cudaStream_t st) {
+    to_bf16_padded_k<<<ceil_div((long)rows_p * cols_p, 256), 256, 0, st>>>(src, rows, cols, dst, rows_p, cols_p);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+}  // namespace svae

@@ -1,0 +1,100 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/svae_b200.h declares (no compute calls without a GPU), and the host mirror of the
+reference module API keeps names, keys and error behaviour."""
+import contextlib
+import io
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as G
+    G.build()
+    import spatial_vae._lib as L
+    return L
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "svae_b200.h")).read()
+    declared = set(re.findall(r"^\s*int\s+(svae_\w+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(built.EXPORTS)
+    for name in declared:
+        assert hasattr(built.lib, name), name
+    assert built.lib.svae_version() >= 100
+
+
+def test_struct_sizes_match_header(built):
+    import ctypes as C
+    assert C.sizeof(built.SvaeShape) == 13 * 4
+    assert C.sizeof(built.SvaeConfig) == 12 * 4
+    assert C.sizeof(built.SvaeDecoderParams) == 8 * (3 + 2 * built.MAX_LAYERS + 2)
+    assert C.sizeof(built.SvaeEncoderParams) == 8 * 2 * (built.MAX_LAYERS + 1)
+
+
+def test_invalid_arguments_return_error_codes_without_a_gpu(built):
+    import ctypes as C
+    s, c = built.SvaeShape(), built.SvaeConfig()
+    s.B, s.P, s.H, s.L, s.C, s.Z, s.I = 4, 16, 32, 2, 5, 2, 5
+    n = C.c_size_t(0)
+    rc = built.lib.svae_workspace_bytes(C.byref(s), C.byref(c), C.byref(n))
+    assert rc == -1 and "n_out" in built.last_error()
+    s.C = 2
+    c.rotate, c.translate, c.likelihood = 1, 1, built.LIK_GAUSS_FITNOISE
+    s.k_ctf = 5
+    rc = built.lib.svae_workspace_bytes(C.byref(s), C.byref(c), C.byref(n))
+    assert rc == -1 and "fit-noise" in built.last_error()      # reference crashes on this combination
+    s.k_ctf = 0
+    assert built.lib.svae_workspace_bytes(C.byref(s), C.byref(c), C.byref(n)) == 0 and n.value > 0
+
+
+def test_module_api_mirrors_reference(built):
+    import spatial_vae.models as M
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        p = M.SpatialGenerator(3, 16, n_out=2, num_layers=3, activation=nn.Tanh)
+        q = M.InferenceNetwork(30, 6, 12, num_layers=2, activation=nn.LeakyReLU)
+    assert "SpatialGenerator" in buf.getvalue() and "InferenceNetwork" in buf.getvalue()   # ctor prints itself
+    assert list(p.state_dict()) == ["coord_linear.weight", "coord_linear.bias", "latent_linear.weight",
+                                    "layers.1.weight", "layers.1.bias", "layers.3.weight", "layers.3.bias",
+                                    "layers.5.weight", "layers.5.bias"]
+    assert list(q.state_dict()) == ["layers.0.weight", "layers.0.bias", "layers.2.weight", "layers.2.bias",
+                                    "layers.4.weight", "layers.4.bias"]
+    assert isinstance(p.layers[-1], nn.Sigmoid) and p.layers[5].out_features == 2
+    # no CPU fallback: CPU tensors fail loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p(torch.zeros(2, 5, 2), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q(torch.zeros(2, 30))
+
+
+def test_same_seed_gives_reference_parameter_init(built):
+    """Parameters are created in the reference's order (coord, latent, hidden..., out), so a
+    golden fixture's seed reproduces its initial state_dict."""
+    import numpy as np
+    import spatial_vae.models as M
+    from tests.helpers import load_case
+    d = load_case("mnist_rt")
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2, activation=nn.Tanh)
+        q = M.InferenceNetwork(30, 6, 12, num_layers=2, activation=nn.Tanh)
+    for k, v in p.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), d["p." + k])
+    for k, v in q.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), d["q." + k])
+
+
+def test_unsupported_options_raise(built):
+    import spatial_vae.models as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, resid=True, num_layers=2)
+    with pytest.raises(NotImplementedError):
+        p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
