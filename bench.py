@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- spatial-VAE train-step throughput on B200 (see the task contract in DESIGN.md section 6).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU port of the reference path
+
+A "step" is one full train step of the hot path on one minibatch of synthetic images:
+gather the shuffled batch -> encoder -> reparameterise -> rotate/translate -> per-pixel decoder ->
+ELBO -> backward -> (allreduce) -> Adam.  Workload at N GPUs: BASELINE.json configs[1]
+(rotated+translated MNIST 28x28, z-dim 100, p-hidden 500x2, minibatch 1024 PER GPU: weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import contextlib
+import io
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spatial-vae_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: family, n (image side), Cin, C_out, Z, H, L, Hq, Lq, batch per GPU, theta_prior, ctf
+    "c1": dict(family="mnist", n=28, Cin=1, C=1, Z=2, H=500, L=2, Hq=500, Lq=2, B=100, theta_prior=math.pi / 4),
+    "c2": dict(family="mnist", n=28, Cin=1, C=1, Z=100, H=500, L=2, Hq=500, Lq=2, B=1024, theta_prior=math.pi / 4),
+    "c3": dict(family="particles", n=40, Cin=1, C=2, Z=2, H=500, L=2, Hq=500, Lq=2, B=512, theta_prior=math.pi),
+    "c4": dict(family="galaxy", n=64, Cin=3, C=3, Z=20, H=1000, L=4, Hq=5000, Lq=2, B=128, theta_prior=math.pi),
+    "c5": dict(family="particles", n=40, Cin=1, C=1, Z=2, H=500, L=2, Hq=500, Lq=2, B=4096, theta_prior=math.pi,
+               ctf=39),
+}
+WORKLOAD_TEXT = {
+    "c1": "train_mnist.py rotated MNIST 28x28, z-dim 2, p-hidden 500x2, minibatch 100",
+    "c2": "rotated+translated MNIST 28x28, z-dim 100, p-hidden 500x2, minibatch 1024 per GPU",
+    "c3": "5HDB-like EM particles 40x40, --fit-noise, minibatch 512 per GPU (no augmentation)",
+    "c4": "galaxy zoo 64x64x3, z-dim 20, p-hidden 1000x4, q-hidden 5000x2, minibatch 128 per GPU",
+    "c5": "CODH/ACS-like EM particles 40x40 with 39x39 CTF kernels, minibatch 4096 per GPU",
+}
+
+
+def flops_per_image_train(c):
+    """Algorithmic FLOPs of one train step per image: every Linear 2*M*K*N forward, x3 for
+    fwd+dX+dW, unpadded H; recompute / padding / elementwise not counted; + CTF 2*2*P*k^2."""
+    P = c["n"] * c["n"]
+    I = c["Z"] + 3
+    dec = P * 2 * (2 * c["H"] + (c["L"] - 1) * c["H"] ** 2 + c["H"] * c["C"]) + 2 * c["Z"] * c["H"]
+    enc = 2 * (P * c["Cin"] * c["Hq"] + (c["Lq"] - 1) * c["Hq"] ** 2 + c["Hq"] * 2 * I)
+    ctf = 2 * 2 * P * c.get("ctf", 0) ** 2
+    return 3 * (dec + enc) + ctf
+
+
+def synth_images(c, count, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    P = c["n"] * c["n"]
+    if c["family"] == "mnist":       # ~80 % exact zeros, values in [0,1]
+        u = torch.rand(count, P, generator=g, device=device)
+        return (u > 0.8).float() * torch.rand(count, P, generator=g, device=device)
+    if c["family"] == "galaxy":
+        return torch.rand(count, P, 3, generator=g, device=device)
+    return torch.randn(count, P, generator=g, device=device)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons streamed (-lms) during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()     # the exact PID we started
+        self.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(mhz)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def cpu_reference_steps(c, batch, steps, warmup, threads):
+    """The oracle port of the reference train step (eval_minibatch + backward + Adam) on host cores."""
+    from oracle import svae_oracle as O
+    torch.set_num_threads(threads)
+    P = c["n"] * c["n"]
+    dec, enc = O.init_params(P * c["Cin"], c["Z"] + 3, c["Z"], c["H"], c["L"], c["Hq"], c["Lq"], c["C"], seed=0)
+    cfg = O.StepConfig(family=c["family"], theta_prior=c["theta_prior"])
+    grid = O.make_grid(c["n"], c["n"])
+    y = synth_images(c, batch, torch.device("cpu"), 1234)
+    ctf = None
+    if c.get("ctf"):
+        ctf = 0.03 * torch.randn(batch, 1, c["ctf"], c["ctf"], generator=torch.Generator().manual_seed(5))
+    adam = O.AdamState(lr=1e-4)
+    times = []
+    for s in range(warmup + steps):
+        eps = torch.randn(batch, c["Z"] + 3, generator=torch.Generator().manual_seed(1000 + s))
+        t0 = time.perf_counter()
+        out, grads = O.step_grads(cfg, dec, enc, grid, y, eps, **({"ctf": ctf} if ctf is not None else {}))
+        new = adam.update(O.flatten_params(dec, enc), grads)
+        dec, enc = O.unflatten_like(dec, enc, new)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def reference_arm(args, c):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = min(c["B"], 64 if c["H"] <= 500 else 4)
+    sec = cpu_reference_steps(c, sample_b, args.steps, max(args.warmup, 1), threads)
+    val = sample_b / sec
+    line = {"impl": "reference", "metric": "train images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.config], "sample": f"{sample_b} images per CPU step"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle port of eval_minibatch+backward+Adam, {sample_b} images/step, "
+                                       f"{args.steps} steps"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def build_models(c, device):
+    import torch.nn as nn
+    import spatial_vae.models as M
+    P = c["n"] * c["n"]
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(c["Z"], c["H"], n_out=c["C"], num_layers=c["L"], activation=nn.Tanh)
+        q = M.InferenceNetwork(P * c["Cin"], c["Z"] + 3, c["Hq"], num_layers=c["Lq"], activation=nn.Tanh)
+    return p.to(device), q.to(device)
+
+
+def time_gemm_kernels(c, rows, device, iters=10):
+    """Device time of the three tcgen05 GEMMs of one hidden layer at the workload's row count,
+    CUDA events on the launching stream (torch's current stream)."""
+    import spatial_vae.functional as SF
+    Hp = (c["H"] + 63) // 64 * 64
+    H = c["H"]
+    A = (torch.randn(rows, Hp, device=device) * 0.5).bfloat16()
+    D = (torch.randn(rows, Hp, device=device) * 0.1).bfloat16()
+    W = (torch.randn(Hp, Hp, device=device) / math.sqrt(H)).bfloat16()
+    bias = torch.zeros(Hp, device=device)
+    out = torch.empty(rows, Hp, device=device, dtype=torch.bfloat16)
+    dW = torch.zeros(H, H, device=device)
+    res = {}
+    calls = {
+        "fwd": lambda: SF.gemm_bf16(0, A, W, M=rows, N=Hp, K=Hp, bias=bias, activation=0, out=out),
+        "dx": lambda: SF.gemm_bf16(1, D, W, M=rows, N=Hp, K=Hp, aux=A, activation=0, out=out),
+        "dw": lambda: SF.gemm_bf16(2, D, A, M=H, N=H, K=rows, out=dW),
+    }
+    for name, fn in calls.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / iters * 1e-3
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    c = dict(CONFIGS[args.config])
+    if args.batch > 0:
+        c["B"] = args.batch
+    if args.impl == "reference":
+        reference_arm(args, c)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import spatial_vae.functional as SF
+    from spatial_vae import _lib as L
+    from spatial_vae.trainer import Trainer
+    from oracle import svae_oracle as O
+
+    P = c["n"] * c["n"]
+    B = c["B"]
+    p_net, q_net = build_models(c, device)
+    spec = SF.StepSpec(family=c["family"], theta_prior=c["theta_prior"], precision=args.precision,
+                       chunk_images=args.chunk)
+    trainer = Trainer(p_net, q_net, spec, lr=1e-4)
+    grid = O.make_grid(c["n"], c["n"]).to(device)
+    n_data = 8 * B
+    data = synth_images(c, n_data, device, 1234 + rank)
+    ctf_all = None
+    if c.get("ctf"):
+        ctf_all = 0.03 * torch.randn(n_data, c["ctf"], c["ctf"], device=device,
+                                     generator=torch.Generator(device=device).manual_seed(77 + rank))
+    perm_gen = torch.Generator(device=device).manual_seed(4321)
+
+    def device_step(i):
+        idx = torch.randperm(n_data, generator=perm_gen, device=device)[:B]
+        y = SF.gather_rows(data, idx)
+        ctf = SF.gather_rows(ctf_all, idx) if ctf_all is not None else None
+        return trainer.step(grid, y, global_batch=B * world, ctf=ctf)
+
+    for i in range(args.warmup):
+        device_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)          # let nvidia-smi attach before the timed region starts
+    launches0 = L.lib.svae_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        res = device_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = L.lib.svae_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    if sampler:
+        sampler.stop()
+    last = [float(v) for v in res.cpu()]
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------------
+    host_data = synth_images(c, 2 * B, torch.device("cpu"), 99 + rank).pin_memory()
+    host_ctf = None
+    if c.get("ctf"):
+        host_ctf = (0.03 * torch.randn(2 * B, c["ctf"], c["ctf"])).pin_memory()
+    out_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        lo = (i % 2) * B
+        y = host_data[lo:lo + B].to(device, non_blocking=True)
+        ctf = host_ctf[lo:lo + B].to(device, non_blocking=True) if host_ctf is not None else None
+        r = trainer.step(grid, y, global_batch=B * world, ctf=ctf)
+        out_host.copy_(r, non_blocking=False)      # device -> host read of the step's result (syncs)
+        return out_host
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    k2 = max(5, args.steps // 2)
+    for i in range(k2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * k2 / float(t_e2e)
+    h2d = B * P * c["Cin"] * 4 + (B * c["ctf"] ** 2 * 4 if c.get("ctf") else 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    burst, sustained, hbm, src = peaks()
+    fl_img = flops_per_image_train(c)
+    line = {
+        "metric": "train images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "fast" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "images_per_gpu": B, "global_batch": B * world,
+                   "precision": args.precision + (" (bf16 tcgen05 hidden GEMMs, fp32 accumulate; everything else fp32)"
+                                                  if args.precision == "fast" else " (fp32 FFMA)"),
+                   "parallelism": f"dp{world}",
+                   "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2) and "
+                         "gathers a fresh shuffled batch"},
+        "pixel_evals_per_s": value * P,
+        "step_tflops_algorithmic": value * fl_img / 1e12,
+        "step_frac_of_sustained_bf16": value * fl_img / 1e12 / (sustained * world),
+        "gpu_launches": int(launches),
+        "last_step": {"elbo": last[0], "logp": last[1], "kl": last[2]},
+        "clocks": sampler.summary() if sampler else None,
+        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+    }
+    if args.precision == "fast" and c["L"] >= 2:
+        rows = B * P
+        kt = time_gemm_kernels(c, rows, device)
+        alg = 2.0 * rows * c["H"] * c["H"]
+        dom = max(kt, key=kt.get)
+        line["roofline"] = {"bound": "tensor", "kernel": f"tc_gemm_kernel<{dom}>", "achieved": alg / kt[dom] / 1e12,
+                            "peak": burst, "unit": "TFLOP/s", "frac": alg / kt[dom] / 1e12 / burst, "traffic": None,
+                            "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {src}",
+                            "all_kernels_tflops": {k: alg / v / 1e12 for k, v in kt.items()},
+                            "all_kernels_ms": {k: v * 1e3 for k, v in kt.items()}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sb = min(B, 64 if c["H"] <= 500 else 4)
+        sec = cpu_reference_steps(c, sb, 5, 2, threads)
+        line["cpu_baseline"] = {"value": sb / sec, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port of eval_minibatch+backward+Adam, {sb} images/step, 5 steps"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,8 @@ typedef struct {
 int  svae_version(void);
 /* copies the last error text of the calling thread into buf (NUL terminated); returns its length */
 int  svae_last_error(char* buf, int n);
+/* kernels launched by this library since it was loaded (all threads); evidence for bench.py */
+unsigned long long svae_launch_count(void);
 /* number of SMs of the current device, <0 on error (used by the host to size row chunks) */
 int  svae_device_sm_count(void);
 

@@ -10,6 +10,8 @@
 namespace svae {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -432,6 +434,8 @@ int svae_last_error(char* buf, int n) {
     }
     return (int)strlen(g_err);
 }
+
+unsigned long long svae_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int svae_device_sm_count(void) {
     int dev = 0, sms = 0;

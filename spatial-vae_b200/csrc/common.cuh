@@ -18,7 +18,13 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         cudaError_t e__ = (call);                                              \
         if (e__ != cudaSuccess) return svae::cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
-#define SVAE_LAUNCH_CHECK() SVAE_CUDA(cudaPeekAtLastError())
+// every kernel launch of the library goes through this macro: it also feeds svae_launch_count()
+void count_launch();
+#define SVAE_LAUNCH_CHECK()                                                    \
+    do {                                                                       \
+        svae::count_launch();                                                  \
+        SVAE_CUDA(cudaPeekAtLastError());                                      \
+    } while (0)
 #define SVAE_TRY(call)                                                         \
     do {                                                                       \
         int r__ = (call);                                                      \

@@ -22,7 +22,7 @@ ACT_CODES = {"tanh": ACT_TANH, "leakyrelu": ACT_LEAKYRELU, "relu": ACT_RELU, "si
 PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST}
 
 EXPORTS = [
-    "svae_version", "svae_last_error", "svae_device_sm_count", "svae_workspace_bytes",
+    "svae_version", "svae_last_error", "svae_launch_count", "svae_device_sm_count", "svae_workspace_bytes",
     "svae_encoder_forward", "svae_encoder_backward", "svae_decoder_forward", "svae_decoder_backward",
     "svae_step", "svae_adam_step", "svae_gather_rows", "svae_gemm_bf16",
 ]
@@ -69,6 +69,7 @@ def _load():
     lib.svae_version.restype = i32
     lib.svae_last_error.argtypes = [C.c_char_p, i32]
     lib.svae_device_sm_count.restype = i32
+    lib.svae_launch_count.restype = C.c_ulonglong
     lib.svae_workspace_bytes.argtypes = [P(SvaeShape), P(SvaeConfig), P(sz)]
     lib.svae_encoder_forward.argtypes = [P(SvaeShape), i32, P(SvaeEncoderParams), vp, vp, vp, vp]
     lib.svae_encoder_backward.argtypes = [P(SvaeShape), i32, P(SvaeEncoderParams), vp, vp, vp, P(SvaeEncoderParams),
@@ -84,7 +85,7 @@ def _load():
     lib.svae_gemm_bf16.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if the library lacks a declared symbol
-        if name not in ("svae_version", "svae_device_sm_count"):
+        if name not in ("svae_version", "svae_device_sm_count", "svae_launch_count"):
             getattr(lib, name).restype = i32
     return lib
 

@@ -210,10 +210,14 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
     cfg = spec.config(shape.C, (1.0 / max(B, 1)) if grad_scale is None else grad_scale)
     nbytes = C.c_size_t(0)
     L.check(L.lib.svae_workspace_bytes(C.byref(shape), C.byref(cfg), C.byref(nbytes)), "svae_workspace_bytes")
+    if B == 0:   # a rank whose slice of a ragged last minibatch is empty: nothing to enqueue
+        return (torch.zeros(0, 3, dtype=torch.float32, device=dev),
+                torch.zeros(0, P, shape.C, dtype=torch.float32, device=dev) if want_y_hat else None,
+                torch.zeros(0, shape.I, dtype=torch.float32, device=dev) if want_latent else None)
     ws = workspace(nbytes.value, dev)
 
-    grid, y, eps = _f32(grid), _f32(y.reshape(B, -1)), _f32(eps)
-    y_enc = _f32(y_enc.reshape(B, -1)) if y_enc is not None else None
+    grid, y, eps = _f32(grid), _f32(y.reshape(B, P * Cin)), _f32(eps)
+    y_enc = _f32(y_enc.reshape(B, P * Cin)) if y_enc is not None else None
     theta_offset = _f32(theta_offset)
     ctf = _f32(ctf)
     mask_u8 = mask.to(torch.uint8).contiguous() if mask is not None else None

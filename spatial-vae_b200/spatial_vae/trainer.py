@@ -1,0 +1,129 @@
+"""Train-step driver: what the reference's train_epoch body does per minibatch
+(train_mnist.py:138-150: eval_minibatch, loss.backward(), optim.step(), optim.zero_grad()),
+as one fused pass over flat parameter / gradient / Adam buffers, data-parallel over the
+ranks of torch.distributed with ONE gradient allreduce per step (NCCL over NVLink on a B200 box,
+gloo in the CPU tests of the host logic).
+
+The nn.Parameters of p_net / q_net are re-pointed at views of one flat fp32 buffer, in the
+optimiser order of the reference (p_net.parameters() then q_net.parameters(), train_mnist.py:387),
+so state_dict()/torch.save keep working and Adam is a single kernel over the flat buffer.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import functional as SF
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous, near-even split of n items over `world` ranks (ragged tail allowed, a rank may
+    get 0 items): the data-parallel partition of one minibatch."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class FlatParams:
+    """Flat fp32 storage for a list of parameters, plus same-shaped flat grad / Adam moments."""
+
+    def __init__(self, params):
+        params = list(params)
+        self.shapes = [p.shape for p in params]
+        self.numels = [p.numel() for p in params]
+        dev = params[0].device
+        # pad every tensor to a multiple of 4 floats so each view is 16-byte aligned
+        self.offsets, off = [], 0
+        for n in self.numels:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.total = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros_like(self.data)
+        self.m = torch.zeros_like(self.data)
+        self.v = torch.zeros_like(self.data)
+        for p, o, n in zip(params, self.offsets, self.numels):
+            self.data[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.data[o:o + n].view(p.shape)
+        self.params = params
+
+    def views(self, flat):
+        return [flat[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+
+
+class Trainer:
+    """One object per process (= per GPU).  `step(y, ...)` runs the whole train step on this rank's
+    slice of the global minibatch and leaves (elbo, logp, kl) batch means on the device."""
+
+    def __init__(self, p_net, q_net, spec: SF.StepSpec, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None):
+        if hasattr(p_net, "_check_supported"):
+            p_net._check_supported()
+        self.p_net, self.q_net, self.spec = p_net, q_net, spec
+        self.lr, self.betas, self.adam_eps = lr, betas, eps
+        self.flat = FlatParams(list(p_net.parameters()) + list(q_net.parameters()))
+        self.t = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self._bind()
+
+    def _bind(self):
+        dec = SF.decoder_tensors_of(self.p_net)
+        enc = SF.encoder_pairs_of(self.q_net)
+        self.dec, self.enc = dec, enc
+        n_dec = len(dec.flat())
+        gv = self.flat.views(self.flat.grad)
+        self.gdec = SF.DecoderTensors.from_flat(gv[:n_dec], dec.latent_w is not None, len(dec.hidden))
+        self.genc = [(gv[n_dec + i], gv[n_dec + i + 1]) for i in range(0, len(gv) - n_dec, 2)]
+
+    # -- one train step ---------------------------------------------------------------------------
+    def step(self, x_coord: torch.Tensor, y_local: torch.Tensor, *, global_batch: Optional[int] = None,
+             eps: Optional[torch.Tensor] = None, y_enc=None, theta_offset=None, ctf=None, mask=None,
+             z_scale: Optional[float] = None) -> torch.Tensor:
+        """y_local: this rank's images.  global_batch: images over all ranks (default: local size x world
+        when every rank holds the same count).  Returns a device tensor [elbo, logp, kl] (global batch
+        means); nothing is synchronised with the host."""
+        B_local = y_local.shape[0]
+        B_global = global_batch if global_batch is not None else B_local * self.world
+        spec = self.spec
+        if z_scale is not None and z_scale != spec.z_scale:
+            spec = SF.StepSpec(**{**spec.__dict__, "z_scale": z_scale})
+        I = self.enc[-1][0].shape[0] // 2
+        if eps is None:
+            eps = torch.empty(B_local, I, dtype=torch.float32, device=y_local.device).normal_()
+        stats, _, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc,
+                                  theta_offset=theta_offset, ctf=ctf, mask=mask, grad_dec=self.gdec,
+                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1))
+        sums = stats.sum(0) if B_local > 0 else stats.new_zeros(3)
+        if self.world > 1:
+            # the one exchange step of the path: gradient sum (+ the three loss sums) across ranks
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+        self.t += 1
+        SF.adam_step(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t, self.betas,
+                     self.adam_eps, zero_grad=True)
+        means = sums / max(B_global, 1)
+        return torch.stack([means[2], means[0], means[1]])
+
+    @torch.no_grad()
+    def evaluate(self, x_coord, y_local, *, global_batch=None, eps=None, ctf=None, mask=None, want_y_hat=False,
+                 z_scale: Optional[float] = None):
+        B_local = y_local.shape[0]
+        B_global = global_batch if global_batch is not None else B_local * self.world
+        spec = self.spec
+        if z_scale is not None and z_scale != spec.z_scale:
+            spec = SF.StepSpec(**{**spec.__dict__, "z_scale": z_scale})
+        I = self.enc[-1][0].shape[0] // 2
+        if eps is None:
+            eps = torch.empty(B_local, I, dtype=torch.float32, device=y_local.device).normal_()
+        stats, y_hat, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, ctf=ctf, mask=mask,
+                                      want_y_hat=want_y_hat)
+        sums = stats.sum(0) if B_local > 0 else stats.new_zeros(3)
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+        means = sums / max(B_global, 1)
+        return torch.stack([means[2], means[0], means[1]]), y_hat

@@ -23,7 +23,7 @@ def built():
 
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "svae_b200.h")).read()
-    declared = set(re.findall(r"^\s*int\s+(svae_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|unsigned long long)\s+(svae_\w+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(built.EXPORTS)
     for name in declared:
