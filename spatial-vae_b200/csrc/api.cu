@@ -181,10 +181,11 @@ struct DecoderCtx {
     __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
 };
 
+// fuse_out: also accumulate the output-layer logits o (rows, C) (pre-filled with out_b) in the epilogue
 template <typename T>
-static int hidden_forward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, int l, int rows);
+static int hidden_forward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, int l, int rows, bool fuse_out);
 template <>
-int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, int l, int rows) {
+int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, int l, int rows, bool) {
     const int H = d.s->H, Hp = d.p->Hp;
     SgemmArgs a{};
     a.A = d.act(l - 1); a.sAm = Hp; a.sAk = 1;
@@ -195,10 +196,13 @@ int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& d
     return sgemm(a, d.st);
 }
 template <>
-int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp, int l, int rows) {
+int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp, int l, int rows,
+                                  bool fuse_out) {
     const int Hp = d.p->Hp;
+    if (fuse_out) SVAE_TRY(fill_rows(d.f(d.p->o), dp.out_b, rows, d.s->C, d.s->C, d.st));
     return tc_gemm(0, rows, Hp, Hp, d.act(l - 1), Hp, d.wbf(l - 1), Hp, dp.hidden_b[l - 1], d.s->H, nullptr, 0,
-                   d.c->activation, d.act(l), Hp, d.st);
+                   d.c->activation, d.act(l), Hp, d.st, fuse_out ? dp.out_w : nullptr, d.s->H, fuse_out ? d.s->C : 0,
+                   fuse_out ? d.f(d.p->o) : nullptr);
 }
 
 template <typename T>
@@ -251,9 +255,12 @@ static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams
     }
     SVAE_TRY(layer0_forward<T>(s, d.c->activation, b0, nb, dp.coord_w, d.f(d.p->hz), grid, d.f(d.p->img), x_explicit,
                                s.H, Hp, d.act(0), d.st));
-    for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows));
-    return out_forward<T>(d.act(s.L - 1), rows, s.H, Hp, s.C, dp.out_w, dp.out_b, d.c->softplus, d.f(d.p->o),
-                          y_hat ? y_hat + (size_t)b0 * s.P * s.C : nullptr, d.st);
+    // FAST precision: the output-layer dot product rides in the epilogue of the last hidden GEMM
+    const bool fuse_out = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3;
+    for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows, fuse_out && l == s.L - 1));
+    float* yh = y_hat ? y_hat + (size_t)b0 * s.P * s.C : nullptr;
+    if (fuse_out) return yh ? logits_to_yhat(d.f(d.p->o), yh, (long)rows * s.C, s.C, d.c->softplus, d.st) : SVAE_OK;
+    return out_forward<T>(d.act(s.L - 1), rows, s.H, Hp, s.C, dp.out_w, dp.out_b, d.c->softplus, d.f(d.p->o), yh, d.st);
 }
 
 // backward over the same chunk given g_o (rows, C) in the workspace: parameter grads, S[b0..]

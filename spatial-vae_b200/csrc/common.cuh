@@ -99,6 +99,7 @@ int sgemm(const SgemmArgs& a, cudaStream_t st);
 
 // ---- bf16 tcgen05 GEMMs (tc_gemm.cu) -----------------------------------------------------------
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
-            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st);
+            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
+            const float* out_w = nullptr, int out_w_ld = 0, int dot_c = 0, float* o_accum = nullptr);
 
 }  // namespace svae

@@ -27,6 +27,9 @@ template <typename T>
 int out_forward(const T* h, int rows, int H, int Hp, int C, const float* out_w, const float* out_b, int softplus,
                 float* o, float* y_hat, cudaStream_t st);
 
+// y_hat = sigmoid(o) (+softplus on channel 0) from stored logits (used when the dot product was fused)
+int logits_to_yhat(const float* o, float* y_hat, long n, int C, int softplus, cudaStream_t st);
+
 // Likelihood per image (train_mnist.py:80-81, train_particles.py:102-139, train_galaxy.py:118-119):
 // reads logits o (nb,P,C), targets, optional CTF kernels and mask; writes stats[b*3+0] = logp_b and
 // g_o (nb,P,C) = grad_scale * d(-logp_b)/do.

@@ -24,6 +24,34 @@ __device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
+// eight adjacent columns of a row: 16-byte (bf16) or 2 x 16-byte (fp32) accesses
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
     v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -38,46 +66,48 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // ------------------------------------------------------------------------------------------------
 // reparameterisation + KL   (train_mnist.py:33-39,62-63,84-86; particles :85-86,99)
 // ------------------------------------------------------------------------------------------------
-__global__ void latent_forward_k(SvaeShape s, SvaeConfig c, const float* __restrict__ zo,
-                                 const float* __restrict__ eps, const float* __restrict__ toff,
-                                 float* __restrict__ lat, float* __restrict__ img, float* __restrict__ zs,
-                                 float* __restrict__ stats) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) latent_forward_k(SvaeShape s, SvaeConfig c, const float* __restrict__ zo,
+                                                        const float* __restrict__ eps, const float* __restrict__ toff,
+                                                        float* __restrict__ lat, float* __restrict__ img,
+                                                        float* __restrict__ zs, float* __restrict__ stats) {
+    // one warp per image, lanes over the I latent dimensions
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= s.B) return;
     const int I = s.I;
     const float* mu = zo + (long)b * 2 * I;
     const float* ls = mu + I;
     const int rot = c.rotate ? 1 : 0;
     const int zcol = rot + (c.translate ? 2 : 0);
-    float kl = 0.f, cs = 1.f, sn = 0.f, dx0 = 0.f, dx1 = 0.f;
-    for (int i = 0; i < I; ++i) {
+    float kl = 0.f;
+    for (int i = lane; i < I; i += 32) {
         const float m = mu[i], l = ls[i];
         const float sd = expf(l);
         const float v = sd * eps[(long)b * I + i] + m;
         if (lat) lat[(long)b * I + i] = v;
         if (rot && i == 0) {
             const float th = v + (toff ? toff[b] : 0.f);
-            cs = cosf(th);
-            sn = sinf(th);
+            img[b * 4 + 0] = cosf(th);
+            img[b * 4 + 1] = sinf(th);
             const float sp = c.theta_prior;
             const float num = c.theta_kl_mean ? (sd * sd + m * m) : (sd * sd);
             kl += -l + logf(sp) + num / 2.f / (sp * sp) - 0.5f;
         } else {
             kl += -l + 0.5f * sd * sd + 0.5f * m * m - 0.5f;
-            if (i < zcol) {
-                if (i - rot == 0) dx0 = v * c.dx_scale; else dx1 = v * c.dx_scale;
-            } else {
-                zs[(long)b * s.Z + (i - zcol)] = v * c.z_scale;
-            }
+            if (i < zcol) img[b * 4 + 2 + (i - rot)] = v * c.dx_scale;
+            else zs[(long)b * s.Z + (i - zcol)] = v * c.z_scale;
         }
     }
-    img[b * 4 + 0] = cs; img[b * 4 + 1] = sn; img[b * 4 + 2] = dx0; img[b * 4 + 3] = dx1;
-    stats[b * 3 + 1] = kl;
+    if (lane == 0) {
+        if (!rot) { img[b * 4 + 0] = 1.f; img[b * 4 + 1] = 0.f; }
+        if (!c.translate) { img[b * 4 + 2] = 0.f; img[b * 4 + 3] = 0.f; }
+    }
+    kl = warp_sum(kl);
+    if (lane == 0) stats[b * 3 + 1] = kl;
 }
 
 int latent_forward(const SvaeShape& s, const SvaeConfig& c, const float* zo, const float* eps,
                    const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st) {
-    latent_forward_k<<<ceil_div(s.B, 128), 128, 0, st>>>(s, c, zo, eps, theta_offset, lat, img, zs, stats);
+    latent_forward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, zo, eps, theta_offset, lat, img, zs, stats);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
@@ -127,6 +157,32 @@ __global__ void __launch_bounds__(256) layer0_k(int P, int act, int b0, const fl
     }
     __syncthreads();
     T* out = h0 + ((long)bl * P + p0) * Hp;
+    if ((Hp & 7) == 0) {
+        // thread = (8-column group, row lane): each row is written with one 16-byte store per thread
+        const int groups = Hp >> 3;
+        for (int g = threadIdx.x % min(groups, 256); g < groups; g += 256) {
+            const int lanes = max(1, 256 / groups);
+            const int rl = threadIdx.x / groups;
+            if (rl >= lanes) break;
+            float w0[8], w1[8], hb[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int n = g * 8 + e;
+                const bool ok = n < H;
+                w0[e] = ok ? coord_w[n * 2 + 0] : 0.f;
+                w1[e] = ok ? coord_w[n * 2 + 1] : 0.f;
+                hb[e] = ok ? hz[(long)b * Hp + n] : 0.f;
+            }
+            for (int r = rl; r < nrows; r += lanes) {
+                const float x0 = sx[r][0], x1 = sx[r][1];
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = act_apply<FAST>(act, fmaf(w0[e], x0, fmaf(w1[e], x1, hb[e])));
+                store8(out + (long)r * Hp + g * 8, v);
+            }
+        }
+        return;
+    }
     for (int n = threadIdx.x; n < Hp; n += blockDim.x) {
         float w0 = 0.f, w1 = 0.f, hb = 0.f;
         if (n < H) {
@@ -232,6 +288,19 @@ int out_forward(const T* h, int rows, int H, int Hp, int C, const float* out_w, 
 }
 template int out_forward<float>(const float*, int, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
 template int out_forward<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, const float*, int, float*, float*, cudaStream_t);
+
+__global__ void logits_to_yhat_k(const float* __restrict__ o, float* __restrict__ y, long n, int C, int softplus) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v, dv;
+    post_output(o[i], (int)(i % C), softplus, v, dv);
+    y[i] = v;
+}
+int logits_to_yhat(const float* o, float* y_hat, long n, int C, int softplus, cudaStream_t st) {
+    logits_to_yhat_k<<<ceil_div(n, 256), 256, 0, st>>>(o, y_hat, n, C, softplus);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // likelihood, one block per image
@@ -364,7 +433,85 @@ int likelihood(const SvaeShape& s, const SvaeConfig& c, int b0, int nb, const fl
 // output-layer backward: thread <-> column pair, loop over rows; no cross-thread reductions
 // ------------------------------------------------------------------------------------------------
 constexpr int OB_ROWS = 128;
-constexpr int OB_MAXPAIRS = 4;   // Hp <= 2048
+constexpr int OB_MAXPAIRS = 4;   // fallback path: Hp <= 2048
+
+// Fast path (Hp % 8 == 0, Hp <= 2048): thread = (8-column group g, row lane rl); a block covers OB_ROWS
+// rows, each thread walks rows rl, rl+lanes, ... with 16-byte loads/stores and keeps its column sums in
+// registers; row lanes are combined through shared memory, then one atomicAdd per column per block.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) out_backward_v8_k(const T* __restrict__ h, const float* __restrict__ g_o,
+                                                         int rows, int H, int Hp, int act,
+                                                         const float* __restrict__ out_w, T* __restrict__ delta,
+                                                         float* __restrict__ d_out_w, float* __restrict__ d_out_b,
+                                                         float* __restrict__ d_b_last) {
+    extern __shared__ float red[];            // lanes x (C+1) x Hp partial column sums
+    __shared__ float sg[OB_ROWS][C];
+    const long r0 = (long)blockIdx.x * OB_ROWS;
+    const int nrows = (int)min((long)OB_ROWS, rows - r0);
+    for (int i = threadIdx.x; i < nrows * C; i += blockDim.x) sg[i / C][i % C] = g_o[r0 * C + i];
+    __syncthreads();
+    const int groups = Hp >> 3;
+    const int lanes = max(1, 256 / groups);
+    const int passes = ceil_div(groups, 256);
+    for (int ps = 0; ps < passes; ++ps) {
+        const int g = ps * 256 + threadIdx.x % min(groups, 256);
+        const int rl = threadIdx.x / groups;
+        const bool active = (g < groups) && (rl < lanes);
+        float w[C][8], aw[C][8], ab[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            ab[e] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                aw[c][e] = 0.f;
+                w[c][e] = (active && g * 8 + e < H) ? out_w[c * H + g * 8 + e] : 0.f;
+            }
+        }
+        if (active) {
+#pragma unroll 2
+            for (int r = rl; r < nrows; r += lanes) {
+                float hv[8], dv[8];
+                load8(h + (r0 + r) * Hp + g * 8, hv);
+                float gc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) gc[c] = sg[r][c];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        t = fmaf(gc[c], w[c][e], t);
+                        aw[c][e] = fmaf(gc[c], hv[e], aw[c][e]);
+                    }
+                    dv[e] = t * act_deriv_from_out(act, hv[e]);
+                    ab[e] += dv[e];
+                }
+                store8(delta + (r0 + r) * Hp + g * 8, dv);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) red[(rl * (C + 1) + c) * Hp + g * 8 + e] = aw[c][e];
+                red[(rl * (C + 1) + C) * Hp + g * 8 + e] = ab[e];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (C + 1) * Hp; i += blockDim.x) {
+            const int c = i / Hp, n = i % Hp;
+            if (n >= H || n / 8 / 256 != ps) continue;
+            float t = 0.f;
+            for (int l = 0; l < lanes; ++l) t += red[(l * (C + 1) + c) * Hp + n];
+            if (c < C) atomicAdd(d_out_w + c * H + n, t);
+            else if (d_b_last) atomicAdd(d_b_last + n, t);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < C) {
+        float t = 0.f;
+        for (int r = 0; r < nrows; ++r) t += sg[r][threadIdx.x];
+        atomicAdd(d_out_b + threadIdx.x, t);
+    }
+}
 
 template <typename T, int C>
 __global__ void __launch_bounds__(256) out_backward_k(const T* __restrict__ h, const float* __restrict__ g_o,
@@ -442,6 +589,22 @@ int out_backward(const T* h, const float* g_o, int rows, int H, int Hp, int C, i
                  T* delta, float* d_out_w, float* d_out_b, float* d_b_last, cudaStream_t st) {
     SVAE_REQUIRE(Hp <= 2 * 256 * OB_MAXPAIRS, SVAE_EINVAL, "hidden width %d too large", Hp);
     const int blocks = ceil_div(rows, OB_ROWS);
+    if ((Hp & 7) == 0) {
+        const int groups = Hp >> 3;
+        const int lanes = groups >= 256 ? 1 : 256 / groups;
+        const size_t smem = (size_t)lanes * (C + 1) * Hp * sizeof(float);
+        if (smem <= 40 * 1024) {
+            switch (C) {
+                case 1: out_backward_v8_k<T, 1><<<blocks, 256, smem, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+                case 2: out_backward_v8_k<T, 2><<<blocks, 256, smem, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+                case 3: out_backward_v8_k<T, 3><<<blocks, 256, smem, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+                case 4: out_backward_v8_k<T, 4><<<blocks, 256, smem, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
+                default: set_error("n_out=%d not supported (1..4)", C); return SVAE_EINVAL;
+            }
+            SVAE_LAUNCH_CHECK();
+            return SVAE_OK;
+        }
+    }
     switch (C) {
         case 1: out_backward_k<T, 1><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
         case 2: out_backward_k<T, 2><<<blocks, 256, 0, st>>>(h, g_o, rows, H, Hp, act, out_w, delta, d_out_w, d_out_b, d_b_last); break;
@@ -462,9 +625,17 @@ constexpr int CS_ROWS = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(256) col_sum_k(const T* __restrict__ src, int rows, int H, int Hp,
-                                                 float* __restrict__ dst) {
-    const long r0 = (long)blockIdx.x * CS_ROWS;
-    const int nrows = (int)min((long)CS_ROWS, rows - r0);
+                                                 float* __restrict__ dst, int rows_per_block) {
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const int nrows = (int)min((long)rows_per_block, rows - r0);
+    if (Hp & 1) {   // odd row stride: no aligned pairs
+        for (int n = threadIdx.x; n < H; n += blockDim.x) {
+            float a = 0.f;
+            for (int r = 0; r < nrows; ++r) a += to_f32(src[(r0 + r) * Hp + n]);
+            atomicAdd(dst + n, a);
+        }
+        return;
+    }
     for (int pr = threadIdx.x; pr < Hp / 2; pr += blockDim.x) {
         float a0 = 0.f, a1 = 0.f;
         for (int r = 0; r < nrows; ++r) {
@@ -478,7 +649,8 @@ __global__ void __launch_bounds__(256) col_sum_k(const T* __restrict__ src, int 
 }
 template <typename T>
 int col_sum(const T* src, int rows, int H, int Hp, float* dst, cudaStream_t st) {
-    col_sum_k<T><<<ceil_div(rows, CS_ROWS), 256, 0, st>>>(src, rows, H, Hp, dst);
+    const int rpb = rows >= 148 * 4 * CS_ROWS ? CS_ROWS : max(8, ceil_div(rows, 148 * 2));
+    col_sum_k<T><<<ceil_div(rows, rpb), 256, 0, st>>>(src, rows, H, Hp, dst, rpb);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }

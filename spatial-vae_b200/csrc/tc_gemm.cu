@@ -8,6 +8,7 @@
 //   mode 1  DX  : out[M,N]  = (A[M,K] W[K,N]) .* act'(aux[M,N])        A K-major,  B MN-major
 //   mode 2  DW  : outf[M,N] += A[Kr,M]^T Bm[Kr,N]  (split over Kr)     A MN-major, B MN-major
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -16,13 +17,20 @@ namespace svae {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64x64 bf16 TMA box (MN-major operands)
-constexpr int MAX_BIAS = 2048;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MAX_BIAS * 4 + 256 + 1024;  // + barriers + align slack
+constexpr int MAX_BIAS = 1024;                // widest hidden layer the epilogue tables hold
+constexpr int MAX_DOT_C = 3;                  // output channels the fused output-layer dot supports
+constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 64-column bf16 epilogue block (SWIZZLE_128B)
+constexpr int OFF_OUT_STAGE = STAGES * STAGE_BYTES;                 // 2 blocks: bf16 output staging for TMA stores
+constexpr int OFF_AUX_STAGE = OFF_OUT_STAGE + 2 * EPI_BLOCK_BYTES;  // 2 blocks: act[l-1] tiles for the dX epilogue
+constexpr int OFF_BIAS = OFF_AUX_STAGE + 2 * EPI_BLOCK_BYTES;
+constexpr int OFF_WO = OFF_BIAS + MAX_BIAS * 4;
+constexpr int OFF_BARS = OFF_WO + MAX_DOT_C * MAX_BIAS * 4;
+constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;                   // + barriers + 1 KB alignment slack
 constexpr int NUM_THREADS = 256;
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
 
@@ -34,6 +42,8 @@ struct TcParams {
     int act;
     void* out; int ldo;
     int vec_red;              // mode 2: 16-byte aligned rows -> red.global.add.v4.f32
+    // mode 0, optional: fused output layer (models.py:84): o_accum[m, c] += sum_n h[m,n] * out_w[c, n]
+    const float* out_w; int out_w_ld; int dot_c; float* o_accum;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -75,6 +85,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -127,39 +146,68 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int m, int
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_const(float a) {
+    if (ACT == SVAE_ACT_TANH) return tanh_fast(a);
+    if (ACT == SVAE_ACT_LEAKYRELU) return a > 0.f ? a : 0.01f * a;
+    if (ACT == SVAE_ACT_RELU) return fmaxf(a, 0.f);
+    return __fdividef(1.f, 1.f + __expf(-a));
+}
+template <int ACT>
+__device__ __forceinline__ float act_deriv_const(float h) {
+    if (ACT == SVAE_ACT_TANH) return fmaf(-h, h, 1.f);
+    if (ACT == SVAE_ACT_LEAKYRELU) return h > 0.f ? 1.f : 0.01f;
+    if (ACT == SVAE_ACT_RELU) return h > 0.f ? 1.f : 0.f;
+    return h * (1.f - h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int MODE>
+// MODE: 0 fwd, 1 dX, 2 dW.  ACT: activation of the epilogue (compile time so the per-element code
+// is branch free).  DOTC: output channels of the fused output-layer dot product (mode 0), 0 = none.
+template <int MODE, int ACT, int DOTC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + MAX_BIAS * 4);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the tmem base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+    float* s_wo = reinterpret_cast<float*>(smem + OFF_WO);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux_full[2], then the tmem base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+    const uint32_t auxfull0 = smem_u32(bars + 2 * STAGES + 4);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (MODE != 2) tma_prefetch_desc(&tmOut);
+        if (MODE == 1) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); mbar_init(auxfull0 + 8 * i, 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    constexpr bool fuse_dot = (MODE == 0) && (DOTC > 0);
     if (MODE == 0) {
         for (int i = threadIdx.x; i < MAX_BIAS; i += NUM_THREADS)
             s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.f;
+        if (fuse_dot) {
+            for (int i = threadIdx.x; i < DOTC * MAX_BIAS; i += NUM_THREADS) {
+                const int c = i / MAX_BIAS, n = i % MAX_BIAS;
+                s_wo[i] = (n < p.bias_n) ? p.out_w[(size_t)c * p.out_w_ld + n] : 0.f;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -232,58 +280,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> (swizzled smem -> TMA store | fp32 reductions) =====
         const int q = warp & 3;                // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;         // row of the 128-row tile owned by this thread
+        const bool leader = (warp == 4 && lane == 0);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mn = tile % (p.m_tiles * p.n_tiles);
-            const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
-            const int m = mt * BM + q * 32 + lane;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        if (MODE == 2) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mn = tile % (p.m_tiles * p.n_tiles);
+                const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
+                const int m = mt * BM + row;
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                const int n = nt * BN + c;
-                if (n >= p.N) break;       // N is a multiple of 64 in modes 0/1; mode 2 masks per element
-                uint32_t v[32];
-                uint4 auxv[4];
-                if (MODE == 1 && m < p.M) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (size_t)m * p.ldaux + n);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) auxv[j] = __ldg(ap + j);
-                }
-                tmem_ld32(t_row + c, v);
-                tmem_ld_wait();
-                if (MODE == 0) {
-                    if (m < p.M) {
-                        uint32_t packed[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float a0 = __uint_as_float(v[2 * j]) + s_bias[n + 2 * j];
-                            const float a1 = __uint_as_float(v[2 * j + 1]) + s_bias[n + 2 * j + 1];
-                            packed[j] = pack_bf16(act_apply<true>(p.act, a0), act_apply<true>(p.act, a1));
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                } else if (MODE == 1) {
-                    if (m < p.M) {
-                        uint32_t packed[16];
-                        const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-                            const float d0 = __uint_as_float(v[2 * j]) * act_deriv_from_out(p.act, __low2float(hv));
-                            const float d1 = __uint_as_float(v[2 * j + 1]) * act_deriv_from_out(p.act, __high2float(hv));
-                            packed[j] = pack_bf16(d0, d1);
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ldo + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                } else {
+                for (int c = 0; c < BN; c += 32) {
+                    const int n = nt * BN + c;
+                    if (n >= p.N) break;
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c, v);
+                    tmem_ld_wait();
                     if (m < p.M) {
                         float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldo + n;
                         if (p.vec_red && n + 32 <= p.N) {
@@ -299,11 +315,120 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        } else {
+            // 64-column blocks: registers -> swizzled staging block -> one TMA store per block.
+            // dX additionally streams the matching act[l-1] block in by TMA, two blocks ahead.
+            uint8_t* out_stage = smem + OFF_OUT_STAGE;
+            uint8_t* aux_stage = smem + OFF_AUX_STAGE;
+            uint32_t blk = 0;                              // running block counter (staging buffer = blk & 1)
+            // prefetch cursor for the aux blocks (leader only)
+            int pf_tile = blockIdx.x, pf_jb = 0; uint32_t pf_blk = 0;
+            auto blocks_in_tile = [&](int tile) {
+                const int nt = (tile % (p.m_tiles * p.n_tiles)) % p.n_tiles;
+                const int left = (p.N - nt * BN) / 64;
+                return left < BN / 64 ? left : BN / 64;
+            };
+            auto prefetch_aux = [&]() {
+                if (pf_tile >= num_tiles) return;
+                const int mn = pf_tile % (p.m_tiles * p.n_tiles);
+                const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
+                const uint32_t bar = auxfull0 + 8 * (pf_blk & 1);
+                mbar_expect_tx(bar, EPI_BLOCK_BYTES);
+                tma_load_2d(smem_u32(aux_stage + (pf_blk & 1) * EPI_BLOCK_BYTES), &tmAux, bar, nt * BN + pf_jb * 64, mt * BM);
+                ++pf_blk;
+                if (++pf_jb == blocks_in_tile(pf_tile)) { pf_jb = 0; pf_tile += gridDim.x; }
+            };
+            if (MODE == 1 && leader) { prefetch_aux(); prefetch_aux(); }
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mn = tile % (p.m_tiles * p.n_tiles);
+                const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
+                const int m = mt * BM + row;
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+                const int nblk = blocks_in_tile(tile);
+                float dot[DOTC > 0 ? DOTC : 1];
+#pragma unroll
+                for (int c = 0; c < (DOTC > 0 ? DOTC : 1); ++c) dot[c] = 0.f;
+#pragma unroll 1
+                for (int jb = 0; jb < nblk; ++jb, ++blk) {
+                    const uint32_t buf = blk & 1;
+                    uint8_t* ostage = out_stage + buf * EPI_BLOCK_BYTES;
+                    const uint8_t* astage = aux_stage + buf * EPI_BLOCK_BYTES;
+                    if (MODE == 1) mbar_wait(auxfull0 + 8 * buf, (blk >> 1) & 1);
+                    // the TMA store issued two blocks ago must have finished READING this staging buffer
+                    if (leader) tma_store_wait_read<1>();
+                    epi_bar_sync();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int n = nt * BN + jb * 64 + half * 32;      // first column of this 32-wide chunk
+                        uint32_t v[32];
+                        tmem_ld32(t_row + jb * 64 + half * 32, v);
+                        uint4 auxv[4];
+                        if (MODE == 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                auxv[j] = *reinterpret_cast<const uint4*>(astage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4));
+                        }
+                        tmem_ld_wait();
+                        uint32_t packed[16];
+                        if (MODE == 0) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {          // 4 columns at a time: 128-bit table reads
+                                const float4 bv = *reinterpret_cast<const float4*>(s_bias + n + 4 * j4);
+                                const float hh[4] = {
+                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 0]) + bv.x),
+                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 1]) + bv.y),
+                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 2]) + bv.z),
+                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 3]) + bv.w)};
+                                packed[2 * j4] = pack_bf16(hh[0], hh[1]);
+                                packed[2 * j4 + 1] = pack_bf16(hh[2], hh[3]);
+                                if (fuse_dot) {
+#pragma unroll
+                                    for (int c = 0; c < DOTC; ++c) {
+                                        const float4 wv = *reinterpret_cast<const float4*>(s_wo + c * MAX_BIAS + n + 4 * j4);
+                                        dot[c] = fmaf(hh[0], wv.x, fmaf(hh[1], wv.y, fmaf(hh[2], wv.z, fmaf(hh[3], wv.w, dot[c]))));
+                                    }
+                                }
+                            }
+                        } else {
+                            const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+                                const float d0 = __uint_as_float(v[2 * j]) * act_deriv_const<ACT>(__low2float(hv));
+                                const float d1 = __uint_as_float(v[2 * j + 1]) * act_deriv_const<ACT>(__high2float(hv));
+                                packed[j] = pack_bf16(d0, d1);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(ostage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) =
+                                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                    fence_proxy_async();           // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    epi_bar_sync();
+                    if (leader) {
+                        tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * 64, mt * BM);   // clips rows >= M
+                        tma_store_commit();
+                        if (MODE == 1) prefetch_aux();     // aux buffer `buf` is free again
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (fuse_dot && m < p.M) {
+#pragma unroll
+                    for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot[c]);
+                }
+            }
+            if (leader) tma_store_wait_read<0>();
         }
     }
 
@@ -352,16 +477,41 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
     return SVAE_OK;
 }
 
-template <int MODE>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, int grid, cudaStream_t st) {
+template <int MODE, int ACT, int DOTC>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x, const TcParams& p,
+           int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        SVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE, ACT, DOTC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES));
         configured = true;
     }
-    tc_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, b, p);
+    tc_gemm_kernel<MODE, ACT, DOTC><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, b, o, x, p);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
+}
+
+template <int MODE, int ACT>
+int launch_dot(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
+               const TcParams& p, int grid, cudaStream_t st) {
+    if (MODE != 0 || p.o_accum == nullptr) return launch<MODE, ACT, 0>(a, b, o, x, p, grid, st);
+    switch (p.dot_c) {
+        case 1: return launch<0, ACT, 1>(a, b, o, x, p, grid, st);
+        case 2: return launch<0, ACT, 2>(a, b, o, x, p, grid, st);
+        default: return launch<0, ACT, 3>(a, b, o, x, p, grid, st);
+    }
+}
+
+template <int MODE>
+int launch_act(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
+               const TcParams& p, int grid, cudaStream_t st) {
+    switch (p.act) {
+        case SVAE_ACT_TANH: return launch_dot<MODE, SVAE_ACT_TANH>(a, b, o, x, p, grid, st);
+        case SVAE_ACT_LEAKYRELU: return launch_dot<MODE, SVAE_ACT_LEAKYRELU>(a, b, o, x, p, grid, st);
+        case SVAE_ACT_RELU: return launch_dot<MODE, SVAE_ACT_RELU>(a, b, o, x, p, grid, st);
+        case SVAE_ACT_SIGMOID: return launch_dot<MODE, SVAE_ACT_SIGMOID>(a, b, o, x, p, grid, st);
+        default: set_error("tc_gemm: unknown activation %d", p.act); return SVAE_EINVAL;
+    }
 }
 
 int sm_count() {
@@ -378,7 +528,8 @@ int sm_count() {
 }  // namespace
 
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
-            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st) {
+            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
+            const float* out_w, int out_w_ld, int dot_c, float* o_accum) {
     SVAE_REQUIRE(mode >= 0 && mode <= 2, SVAE_EINVAL, "tc_gemm: unknown mode %d", mode);
     if (M <= 0 || N <= 0 || K <= 0) return SVAE_OK;
     TcParams p{};
@@ -390,18 +541,26 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     p.k_blocks = ceil_div(K, BK);
     p.k_splits = 1;
     p.k_blocks_per_split = p.k_blocks;
-    CUtensorMap ma, mb;
+    p.out_w = out_w; p.out_w_ld = out_w_ld; p.dot_c = dot_c; p.o_accum = o_accum;
+    CUtensorMap ma, mb, mo, mx;
+    memset(&mo, 0, sizeof(mo));
+    memset(&mx, 0, sizeof(mx));
     const int sms = sm_count();
     if (mode == 0) {
-        SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0 && N <= MAX_BIAS, SVAE_EINVAL, "tc_gemm fwd: N, K must be multiples of 64");
+        SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0 && N <= MAX_BIAS, SVAE_EINVAL, "tc_gemm fwd: N, K must be multiples of 64 and N <= %d", MAX_BIAS);
         SVAE_REQUIRE(ldo % 8 == 0, SVAE_EALIGN, "tc_gemm: output leading dimension %% 8 != 0");
+        SVAE_REQUIRE(o_accum == nullptr || (mode == 0 && dot_c >= 1 && dot_c <= MAX_DOT_C && out_w != nullptr),
+                     SVAE_EINVAL, "tc_gemm fwd: fused output dot supports 1..%d channels", MAX_DOT_C);
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, N, K, ldw, 64, 256));
+        SVAE_TRY(make_map(&mo, out, M, N, ldo, 64, 128));
     } else if (mode == 1) {
         SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm dx: N, K must be multiples of 64");
         SVAE_REQUIRE(ldo % 8 == 0 && ldaux % 8 == 0 && aux != nullptr, SVAE_EALIGN, "tc_gemm dx: aux/out alignment");
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, K, N, ldw, 64, 64));
+        SVAE_TRY(make_map(&mo, out, M, N, ldo, 64, 128));
+        SVAE_TRY(make_map(&mx, aux, M, N, ldaux, 64, 128));
     } else {
         // A: (K rows) x (lda cols) with M <= lda logical columns; Bm: (K rows) x (ldw cols), N <= ldw
         SVAE_TRY(make_map(&ma, A, K, round_up(M, 64) <= lda ? round_up(M, 64) : lda, lda, 64, 64));
@@ -416,9 +575,9 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     }
     const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
     const int grid = tiles < sms ? tiles : sms;
-    if (mode == 0) return launch<0>(ma, mb, p, grid, st);
-    if (mode == 1) return launch<1>(ma, mb, p, grid, st);
-    return launch<2>(ma, mb, p, grid, st);
+    if (mode == 0) return launch_act<0>(ma, mb, mo, mx, p, grid, st);
+    if (mode == 1) return launch_act<1>(ma, mb, mo, mx, p, grid, st);
+    return launch<2, SVAE_ACT_TANH, 0>(ma, mb, mo, mx, p, grid, st);
 }
 
 }  // namespace svae
