@@ -1,0 +1,321 @@
+"""Shared machinery of the three command lines (train_mnist.py, train_particles.py, train_galaxy.py).
+
+The reference triplicates eval_minibatch / train_epoch / eval_model in each script
+(train_mnist.py:24-226, train_particles.py:22-245, train_galaxy.py:27-294); here the three scripts
+are thin flag definitions over this module.  The per-minibatch work is one fused call
+(spatial_vae.functional.elbo_step or, in the epoch loops, spatial_vae.trainer.Trainer.step); the
+batch-size-weighted running means the reference keeps on the host with three .item() syncs per
+step (train_mnist.py:152-164) are kept on the device and read once per progress update.
+"""
+from __future__ import annotations
+
+import datetime
+import math
+import os
+import sys
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as SF
+from . import models
+from .trainer import Trainer, shard_bounds
+
+
+# --------------------------------------------------------------------------------------------------
+# eval_minibatch: same signatures and return values as the reference functions
+# --------------------------------------------------------------------------------------------------
+def _spec_for(family, p_net, rotate, translate, dx_scale, theta_prior, z_scale=1.0, precision=None):
+    return SF.StepSpec(family=family, rotate=bool(rotate), translate=bool(translate), dx_scale=float(dx_scale),
+                       theta_prior=float(theta_prior), z_scale=float(z_scale),
+                       activation=getattr(p_net, "activation_code", 0), softplus=bool(getattr(p_net, "softplus", False)),
+                       precision=precision or getattr(p_net, "precision", None) or SF.default_precision())
+
+
+def _is_spatial(p_net):
+    return isinstance(p_net, models.SpatialGenerator)
+
+
+def eval_minibatch_mnist(x, y, p_net, q_net, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+                         use_cuda=False, eps=None):
+    """train_mnist.eval_minibatch (reference train_mnist.py:24-90) -> (elbo, log_p_x_g_z, kl_div, y_hat)."""
+    if use_cuda:
+        y = y.cuda()
+    spec = _spec_for("mnist", p_net, rotate, translate, dx_scale, theta_prior)
+    elbo, logp, kl, y_hat, _ = SF.elbo_step(spec, x, y, p_net, q_net, eps=eps, want_y_hat=True)
+    return elbo, logp, kl, y_hat.view(y.size(0), -1)
+
+
+def rotate_images_bicubic(y, n, offsets, channels=None):
+    """The reference's host-side augmentation (train_particles.py:36-43 / train_galaxy.py:44-54): PIL
+    bicubic rotation per image.  Host code on purpose: the device kernel is a listed next step
+    (SURVEY.md section 8f rank 1), the arithmetic lives in Pillow."""
+    from PIL import Image
+    out = y.clone()
+    for i in range(y.size(0)):
+        deg = 360 * offsets[i] / 2 / np.pi
+        if channels is None:
+            im = Image.fromarray(y[i].view(n, n).cpu().numpy())
+            im = im.rotate(deg, resample=Image.BICUBIC)
+            out[i] = torch.from_numpy(np.array(im)).to(y.device).view(-1)
+        else:
+            im = Image.fromarray((y[i].view(n, n, channels).cpu().numpy() * 255).astype(np.uint8))
+            im = im.rotate(deg, resample=Image.BICUBIC)
+            out[i] = torch.from_numpy(np.array(im).astype(float) / 255).to(y.device).view(-1, channels)
+    return out
+
+
+def _augment(y, rotate, augment_rotation, channels=None):
+    b = y.size(0)
+    n = int(np.sqrt(y.size(1)))
+    if not (rotate and augment_rotation):
+        return None, None
+    offset = np.random.uniform(0, 2 * np.pi, size=b)       # unseeded numpy RNG, as in the reference
+    if rotate < 1:
+        offset *= np.random.binomial(1, p=rotate, size=b)
+    y_rot = rotate_images_bicubic(y, n, offset, channels)
+    return y_rot, torch.from_numpy(offset).float().to(y.device)
+
+
+def eval_minibatch_particles(x, y, mask, ctf, p_net, q_net, rotate=True, translate=True, dx_scale=0.1,
+                             theta_prior=np.pi, augment_rotation=False, z_scale=1, use_cuda=False, eps=None):
+    """train_particles.eval_minibatch (reference train_particles.py:22-148) -> (elbo, log_p_x_g_z, kl_div)."""
+    y_rot, offset = _augment(y, rotate, augment_rotation)
+    if use_cuda:
+        y = y.cuda()
+        y_rot = y_rot.cuda() if y_rot is not None else None
+    if ctf is not None and p_net.layers[-2].out_features > 1:
+        # the reference's variance convolution lacks groups= and crashes here (train_particles.py:121-124,137)
+        raise RuntimeError("CTF filtering cannot be combined with --fit-noise (the reference raises as well)")
+    spec = _spec_for("particles", p_net, rotate, translate, dx_scale, theta_prior, z_scale)
+    elbo, logp, kl, _, _ = SF.elbo_step(spec, x, y, p_net, q_net, eps=eps, y_enc=y_rot, theta_offset=offset,
+                                        ctf=ctf.reshape(ctf.size(0), ctf.size(-2), ctf.size(-1)) if ctf is not None else None,
+                                        mask=mask)
+    return elbo, logp, kl
+
+
+def eval_minibatch_galaxy(x, y, p_net, q_net, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+                          augment_rotation=False, z_scale=1, use_cuda=False, eps=None):
+    """train_galaxy.eval_minibatch (reference train_galaxy.py:27-128) -> (elbo, log_p_x_g_z, kl_div, y_hat)."""
+    channels = y.size(2)
+    y_rot, offset = _augment(y, rotate, augment_rotation, channels)
+    if use_cuda:
+        y = y.cuda()
+        y_rot = y_rot.cuda() if y_rot is not None else None
+    spec = _spec_for("galaxy", p_net, rotate, translate, dx_scale, theta_prior, z_scale)
+    elbo, logp, kl, y_hat, _ = SF.elbo_step(spec, x, y, p_net, q_net, eps=eps, y_enc=y_rot, theta_offset=offset,
+                                            want_y_hat=True)
+    return elbo, logp, kl, y_hat.view(y.size(0), -1, channels)
+
+
+def minibatch_for_display(x, y, p_net, q_net, rotate=True, translate=True, z_scale=1, use_cuda=False):
+    """Decode the sampled z on the UNrotated grid (reference train_mnist.py:93-124, train_galaxy.py:131-163)."""
+    batch = y.size(0)
+    if use_cuda:
+        y = y.cuda()
+    with torch.no_grad():
+        z_mu, z_logstd = q_net(y.reshape(batch, -1))
+        r = torch.empty_like(z_mu).normal_()
+        z = torch.exp(z_logstd) * r + z_mu
+        if rotate:
+            z = z[:, 1:]
+        if translate:
+            z = z[:, 2:]
+        z = z * z_scale
+        y_hat = p_net(x.expand(batch, x.size(0), x.size(1)).contiguous(), z.contiguous())
+    return y_hat.view(batch, -1) if y.dim() == 2 else y_hat.view(batch, -1, y.size(2))
+
+
+def random_minibatch_generator(x, y, p_net, z_dim, z_scale=1, use_cuda=False):
+    """Decode z ~ N(0, I) (reference train_galaxy.py:166-183)."""
+    batch = y.size(0)
+    with torch.no_grad():
+        z = torch.empty(batch, z_dim, device=x.device).normal_() * z_scale
+        y_hat = p_net(x.expand(batch, x.size(0), x.size(1)).contiguous(), z)
+    return y_hat.view(batch, -1, y.size(2)) if y.dim() == 3 else y_hat.view(batch, -1)
+
+
+# --------------------------------------------------------------------------------------------------
+# epoch loops
+# --------------------------------------------------------------------------------------------------
+def make_grid(n_rows, n_cols, device=None):
+    """(P,2) pixel coordinates, x in [-1,1] along columns, y from +1 down to -1 along rows
+    (reference train_mnist.py:316-320)."""
+    xs = np.linspace(-1, 1, n_cols)
+    ys = np.linspace(1, -1, n_rows)
+    x0, x1 = np.meshgrid(xs, ys)
+    g = torch.from_numpy(np.stack([x0.ravel(), x1.ravel()], 1)).float()
+    return g.to(device) if device is not None else g
+
+
+class RunningMeans:
+    """Batch-size-weighted running means of (elbo, error, kl) kept on the device
+    (the reference's host arithmetic at train_mnist.py:156-164)."""
+
+    def __init__(self, device):
+        self.sums = torch.zeros(3, dtype=torch.float64, device=device)
+        self.count = 0
+
+    def update(self, means: torch.Tensor, n: int):
+        self.sums += means.double() * n
+        self.count += n
+
+    def read(self):
+        m = (self.sums / max(self.count, 1)).tolist()
+        return m[0], -m[1], m[2]      # elbo, error = -log p(x|z), kl
+
+
+def epoch_permutation(n, shuffle, generator):
+    return torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+
+
+def run_epoch(trainer: Trainer, x_coord, data, *, train: bool, minibatch_size: int, generator=None, ctf=None,
+              mask=None, augment=None, z_scale=None, epoch=0, num_epochs=1, progress=True, first_batch_hook=None):
+    """One pass over `data` (N, ...) resident on the device.  Every rank walks the same permutation
+    (same CPU generator seed) and takes its contiguous slice of each minibatch; the last minibatch may
+    be ragged (DataLoader(drop_last=False), reference train_mnist.py:395)."""
+    N = data.shape[0]
+    dev = data.device
+    perm = epoch_permutation(N, train, generator)
+    means = RunningMeans(dev)
+    world, rank = trainer.world, trainer.rank
+    for start in range(0, N, minibatch_size):
+        idx = perm[start:start + minibatch_size]
+        bsz = idx.numel()
+        lo, hi = shard_bounds(bsz, world, rank)
+        idx_local = idx[lo:hi].to(dev)
+        y = SF.gather_rows(data, idx_local)
+        c = SF.gather_rows(ctf, idx_local) if ctf is not None else None
+        if train:
+            y_enc = theta_offset = None
+            if augment is not None:
+                y_enc, theta_offset = augment(y)
+            res = trainer.step(x_coord, y, global_batch=bsz, y_enc=y_enc, theta_offset=theta_offset, ctf=c, mask=mask,
+                               z_scale=z_scale)
+        else:
+            want = first_batch_hook is not None and start == 0
+            res, y_hat = trainer.evaluate(x_coord, y, global_batch=bsz, ctf=c, mask=mask, want_y_hat=want,
+                                          z_scale=z_scale)
+            if want:
+                first_batch_hook(y, y_hat)
+        means.update(res, bsz)
+        if progress and train and rank == 0 and (start // minibatch_size) % 20 == 0:
+            e, err, kl = means.read()
+            line = '# [{}/{}] training {:.1%}, ELBO={:.5f}, Error={:.5f}, KL={:.5f}'.format(
+                epoch + 1, num_epochs, means.count / N, e, err, kl)
+            print(line, end='\r', file=sys.stderr)
+    if progress and train and rank == 0:
+        print(' ' * 80, end='\r', file=sys.stderr)
+    return means.read()
+
+
+# --------------------------------------------------------------------------------------------------
+# run bookkeeping (reference src/misc_tools.py, src/file_tools.py): thin, behaviour compatible
+# --------------------------------------------------------------------------------------------------
+def activation_from_flag(name, script):
+    """'relu' means LeakyReLU in mnist/particles (train_mnist.py:344-348) but true ReLU in galaxy, whose
+    'leakyrelu' choice silently stays Tanh (typo at train_galaxy.py:429)."""
+    if script in ("mnist", "particles"):
+        return nn.Tanh if name == "tanh" else nn.LeakyReLU
+    return {"tanh": nn.Tanh, "relu": nn.ReLU, "sigmoid": nn.Sigmoid}.get(name, nn.Tanh)
+
+
+def pick_device(d):
+    """-d flag (reference train_mnist.py:323-327): -1 = CPU (not supported here), -2 = current CUDA device."""
+    if d == -1 or not torch.cuda.is_available():
+        raise SystemExit("this build of spatial-VAE runs on NVIDIA B200 GPUs only (no CPU path); "
+                         "use the reference implementation for CPU runs")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if d >= 0:
+        local = d
+        print('# using CUDA device:', d, file=sys.stderr)
+    torch.cuda.set_device(local)
+    return torch.device("cuda", local)
+
+
+def init_distributed(device):
+    """One process per GPU under torchrun; single process otherwise."""
+    import torch.distributed as dist
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def prepare_output_dir(args, assume_yes=False):
+    """outputs_<prefix>/{trained,images} wiped and recreated, command.txt written
+    (reference misc_tools.py:48-74).  The reference blocks on input(); --yes or a non-tty skips it."""
+    if not assume_yes and sys.stdin.isatty():
+        if input('WARNING Will clear the outputs directory if it exists. Continue (y/n and Enter)?').lower() == 'n':
+            raise SystemExit(0)
+    import shutil
+    start = datetime.datetime.now()
+    print(f"Start : {start.strftime('%y%m%d_%H%M%S')}")
+    out = 'outputs_{}'.format(args.save_prefix)
+    trained, images = os.path.join(out, 'trained'), os.path.join(out, 'images')
+    if os.path.isdir(out):
+        shutil.rmtree(out)
+    for d in (out, trained, images):
+        os.makedirs(d, exist_ok=True)
+    with open(os.path.join(out, 'command.txt'), 'w') as f:
+        for k, v in vars(args).items():
+            print(f'{k}: {v}', file=f)
+    digits = int(np.log10(args.num_epochs)) + 1
+    return start, out, trained, images, digits
+
+
+def save_label(args):
+    """reference misc_tools.py:15-28"""
+    names = {'z_dim': 'z', 'p_num_layers': 'pnl', 'q_num_layers': 'qnl', 'num_layers': 'nl', 'num_epochs': 'ep'}
+    label = str(args.save_prefix) + '_'
+    for k, v in vars(args).items():
+        if k in names:
+            label += names[k] + str(v)
+    return label
+
+
+def save_models(path_prefix, epoch_str, trained_dir, p_net, q_net, device):
+    """Whole-module pickles *_generator_epochN.sav / *_inference_epochN.sav, saved from CPU in eval mode
+    (reference misc_tools.py:87-104, train_particles.py:530-543).  The saved copies are detached
+    clones so the trainer's flat parameter buffer stays on the device."""
+    import copy
+    if path_prefix is None:
+        return
+    for net, tag in ((p_net, 'generator'), (q_net, 'inference')):
+        path = path_prefix + '_{}_epoch{}.sav'.format(tag, epoch_str)
+        if trained_dir:
+            path = os.path.join(trained_dir, path)
+        clone = copy.deepcopy(net).eval().cpu()
+        torch.save(clone, path)
+
+
+def export_batch_as_image(data, output, image_dims, channels_last=True):
+    """PNG grid of a batch (reference misc_tools.py:30-39); needs torchvision."""
+    try:
+        from torchvision.utils import save_image
+    except Exception:      # torchvision is optional in this build
+        return
+    images = data.view(data.size(0), *image_dims, -1)
+    if channels_last:
+        images = images.permute(0, 3, 1, 2)
+    save_image(images.cpu(), output, nrow=int(data.size(0) ** 0.5), padding=3, pad_value=0.5)
+
+
+def add_b200_flags(parser, hyphen=False):
+    """Flags this build adds on top of the reference's."""
+    sep = '-' if hyphen else '_'
+    parser.add_argument('--precision', choices=['fast', 'parity'], default='fast',
+                        help='fast: bf16 tcgen05 hidden GEMMs with fp32 accumulation; parity: fp32 FFMA everywhere')
+    parser.add_argument('--seed', type=int, default=None, help='seed torch (and the shuffling) for reproducible runs')
+    parser.add_argument('--yes', action='store_true', help='do not prompt before clearing the outputs directory')
+    parser.add_argument(f'--synthetic', type=int, default=0,
+                        help='train on this many synthetic images of the dataset\'s shape instead of loading files')
+    parser.add_argument(f'--synthetic{sep}size', type=int, default=0, help='image side for --synthetic')
+
+
+def write_results(output_dir, train_lines, val_lines):
+    with open(os.path.join(output_dir, 'train.txt'), 'w') as f:
+        print('\n'.join(train_lines), file=f)
+    with open(os.path.join(output_dir, 'val.txt'), 'w') as f:
+        print('\n'.join(val_lines), file=f)

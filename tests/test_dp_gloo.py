@@ -1,0 +1,138 @@
+"""Host-side data-parallel logic on CPU with the gloo backend, world_size 2.
+
+The kernels cannot run here, so the two library calls of Trainer.step (run_step, adam_step) are
+replaced by test doubles built on the CPU oracle; everything else is the product code: flat
+parameter/gradient buffers behind the nn.Parameters, the contiguous ragged sharding of a minibatch,
+grad_scale = 1/B_global, the one gradient allreduce and the loss-sum allreduce, replicated Adam.
+The result must equal the single-process oracle trajectory on the full minibatch.
+"""
+import contextlib
+import io
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import svae_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _install_doubles(SF):
+    def fake_run_step(spec, dec, enc, grid, y, eps, *, y_enc=None, theta_offset=None, ctf=None, mask=None,
+                      grad_dec=None, grad_enc=None, grad_scale=None, want_y_hat=False, want_latent=False):
+        B = y.shape[0]
+        if B == 0:
+            return torch.zeros(0, 3), None, None
+        cfg = O.StepConfig(family=spec.family, rotate=spec.rotate, translate=spec.translate, dx_scale=spec.dx_scale,
+                           theta_prior=spec.theta_prior, z_scale=spec.z_scale)
+        d = {"coord_w": dec.coord_w.detach(), "coord_b": dec.coord_b.detach(),
+             "latent_w": dec.latent_w.detach() if dec.latent_w is not None else None,
+             "hidden": [(w.detach(), b.detach()) for w, b in dec.hidden], "out_w": dec.out_w.detach(),
+             "out_b": dec.out_b.detach()}
+        e = [(w.detach(), b.detach()) for w, b in enc]
+        out, grads = O.step_grads(cfg, d, e, grid, y, eps)
+        if grad_dec is not None:
+            scale = (grad_scale if grad_scale is not None else 1.0 / B) * B    # oracle grads are of the batch MEAN
+            targets = grad_dec.flat() + [t for pair in grad_enc for t in pair]
+            for t, g in zip(targets, grads):
+                t.add_(g * scale)
+        stats = torch.stack([out["logp_i"], out["kl_i"], out["logp_i"] - out["kl_i"]], 1)
+        return stats, None, None
+
+    def fake_adam(param, grad, m, v, lr, t, betas=(0.9, 0.999), eps=1e-8, zero_grad=True):
+        m.mul_(betas[0]).add_(grad, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(grad, grad, value=1 - betas[1])
+        bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
+        param.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+        if zero_grad:
+            grad.zero_()
+
+    SF.run_step = fake_run_step
+    SF.adam_step = fake_adam
+
+
+def _worker(rank, world, port, batches, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import spatial_vae.functional as SF
+        import spatial_vae.models as M
+        from spatial_vae.trainer import Trainer, shard_bounds
+        _install_doubles(SF)
+        torch.manual_seed(3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2)
+            q = M.InferenceNetwork(36, 6, 12, num_layers=2)
+        spec = SF.StepSpec(family="mnist", theta_prior=0.7, precision="parity")
+        tr = Trainer(p, q, spec, lr=1e-3)
+        assert tr.world == world and tr.rank == rank
+        grid = O.make_grid(6, 6)
+        losses = []
+        for y, eps in batches:
+            lo, hi = shard_bounds(y.shape[0], world, rank)
+            res = tr.step(grid, y[lo:hi], global_batch=y.shape[0], eps=eps[lo:hi])
+            losses.append(res.clone())
+        # parameters are views of the flat buffer and identical on every rank
+        assert p.coord_linear.weight.data_ptr() == tr.flat.data.data_ptr()
+        flat = tr.flat.data.clone()
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert all(torch.equal(gathered[0], g) for g in gathered)
+        if rank == 0:
+            torch.save({"state_p": p.state_dict(), "state_q": q.state_dict(), "losses": torch.stack(losses)}, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def _batches():
+    g = torch.Generator().manual_seed(5)
+    out = []
+    for B in (5, 4, 1):        # ragged split 3+2, even split, and a rank with an empty slice
+        y = (torch.rand(B, 36, generator=g) > 0.7).float() * torch.rand(B, 36, generator=g)
+        out.append((y, torch.randn(B, 6, generator=g)))
+    return out
+
+
+def test_two_rank_trainer_matches_single_process_oracle(tmp_path):
+    batches = _batches()
+    tmp = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(2, _free_port(), batches, tmp), nprocs=2, join=True)
+    got = torch.load(tmp)
+
+    # single-process oracle trajectory on the full minibatches, from the same initial parameters
+    import spatial_vae.models as M
+    torch.manual_seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2)
+        q = M.InferenceNetwork(36, 6, 12, num_layers=2)
+    dec = O.decoder_params_from_state({k: v.clone() for k, v in p.state_dict().items()})
+    enc = O.encoder_params_from_state({k: v.clone() for k, v in q.state_dict().items()})
+    cfg = O.StepConfig(family="mnist", theta_prior=0.7)
+    dec2, enc2, elbos = O.train_steps(cfg, dec, enc, O.make_grid(6, 6), [b[0] for b in batches],
+                                      [b[1] for b in batches], lr=1e-3)
+    np.testing.assert_allclose(got["losses"][:, 0].numpy(), elbos, rtol=1e-5)
+    ref = O.flatten_params(dec2, enc2)
+    mine = list(got["state_p"].values()) + list(got["state_q"].values())
+    for a, b in zip(mine, ref):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_shard_bounds_cover_and_are_contiguous():
+    from spatial_vae.trainer import shard_bounds
+    for n in (0, 1, 5, 8, 1023, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= max(1, (n + w - 1) // w)

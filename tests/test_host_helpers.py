@@ -1,0 +1,79 @@
+"""CPU tests of the host-side pieces around the hot path: CLI flag surfaces, CTF kernels, MRC IO."""
+import io
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import load_case
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spatial-vae_b200")
+
+
+def test_ctf_kernels_match_reference_fixture():
+    import pandas as pd
+    import spatial_vae.ctf as C
+    d = load_case("ctf_kernels")
+    table = pd.DataFrame({k: d[k] for k in C.CTF_COLUMNS})
+    k = C.ctf_filter(table, int(d["n"]), int(d["m"]))
+    np.testing.assert_allclose(k, d["kernels"], rtol=1e-5, atol=1e-7)
+
+
+def test_ctf_table_parser(tmp_path):
+    import spatial_vae.ctf as C
+    path = tmp_path / "ctf.txt"
+    path.write_text("1.5 2.7 300 2.5 100 10 0 45\n2.0  2.7 300 2.5 100 10 0 90\n")
+    t = C.parse_ctf(str(path))
+    assert list(t.columns) == C.CTF_COLUMNS and len(t) == 2 and t.defocus[1] == 2.0
+
+
+def test_mrc_roundtrip_and_crop():
+    import spatial_vae.mrc as M
+    from spatial_vae.image import crop
+    a = np.random.default_rng(0).random((4, 6, 8)).astype(np.float32)
+    buf = io.BytesIO()
+    M.write(buf, a)
+    b, header, ext = M.parse(buf.getvalue())
+    assert np.array_equal(a, b) and (header.nx, header.ny, header.nz, header.mode) == (8, 6, 4, 2) and ext == b""
+    assert crop(a, 4).shape == (4, 4, 4) and np.array_equal(crop(a, 4), a[:, 1:5, 2:6])
+
+
+def _load_script(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(PKG, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_cli_flags_keep_reference_names_and_defaults():
+    mn = _load_script("train_mnist")
+    a = mn.mnist_arguments([])
+    assert (a.z_dim, a.p_hidden_dim, a.q_hidden_dim, a.num_layers, a.minibatch_size) == (2, 500, 500, 2, 100)
+    assert a.theta_prior == pytest.approx(math.pi / 4) and a.dx_scale == 0.1 and a.learning_rate == 1e-4
+    assert a.dataset == "mnist-rotated-translated" and a.device == -2 and a.val_split == 50
+    b = mn.mnist_arguments(["--z-dim", "7", "--no_rotate", "--minibatch-size", "64"])   # both spellings
+    assert b.z_dim == 7 and b.no_rotate and b.minibatch_size == 64
+
+    pt = _load_script("train_particles")
+    c = pt.parse(["tr.npy", "te.npy", "--fit-noise", "--augment-rotation", "--minibatch-size", "512"])
+    assert c.fit_noise and c.augment_rotation and c.minibatch_size == 512 and c.theta_prior == pytest.approx(math.pi)
+    assert (c.p_hidden_dim, c.p_num_layers, c.q_hidden_dim, c.q_num_layers, c.z_delay) == (500, 2, 500, 2, 0)
+
+    gx = _load_script("train_galaxy")
+    g = gx.galaxy_arguments(["tr.npy", "te.npy", "-z", "20", "--p_hidden_dim", "1000", "--p_num_layers", "4"])
+    assert (g.z_dim, g.p_hidden_dim, g.p_num_layers, g.q_hidden_dim) == (20, 1000, 4, 5000)
+    assert g.theta_prior == pytest.approx(math.pi) and g.activation == "tanh"
+    # the scripts export the reference's function names
+    for mod in (mn, pt, gx):
+        assert callable(mod.eval_minibatch) and callable(mod.main)
+
+
+def test_activation_flag_quirks():
+    import torch.nn as nn
+    from spatial_vae import driver as D
+    assert D.activation_from_flag("relu", "mnist") is nn.LeakyReLU      # reference train_mnist.py:344-348
+    assert D.activation_from_flag("relu", "galaxy") is nn.ReLU          # reference train_galaxy.py:431-432
+    assert D.activation_from_flag("leakyrelu", "galaxy") is nn.Tanh     # typo at train_galaxy.py:429
