@@ -249,12 +249,11 @@ class _FusedElbo(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, n_dec, aux, *params):
-        grid, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat = aux
+        grid, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad = aux
         dec_flat, enc_flat = params[:n_dec], params[n_dec:]
         has_latent = (n_dec % 2 == 1)
         dec = DecoderTensors.from_flat([p.detach() for p in dec_flat], has_latent, (n_dec - 4 - int(has_latent)) // 2)
         enc = [(enc_flat[i].detach(), enc_flat[i + 1].detach()) for i in range(0, len(enc_flat), 2)]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         gd = ge = None
         if need_grad:
             gflat = [torch.zeros_like(p, dtype=torch.float32) for p in params]
@@ -297,7 +296,9 @@ def elbo_step(spec: StepSpec, x_coord, y, p_net, q_net, *, eps=None, y_enc=None,
         eps = torch.empty(B, I, dtype=torch.float32, device=x_coord.device).normal_()
     dflat = dec.flat()
     eflat = [t for pair in enc for t in pair]
-    aux = (x_coord, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat)
+    # autograd Functions run their forward with grad mode off, so decide here whether the backward is wanted
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in dflat + eflat)
+    aux = (x_coord, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad)
     elbo, logp, kl, y_hat, stats = _FusedElbo.apply(spec, len(dflat), aux, *dflat, *eflat)
     return elbo, logp, kl, (y_hat if want_y_hat else None), stats
 
