@@ -69,39 +69,44 @@ def synth_images(c, count, device, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons streamed (-lms) during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML during the timed region.  (Streaming
+    `nvidia-smi -lms` from a side process stalled NCCL steps on multi-GPU runs; the in-process NVML
+    queries of ONE device do not.)"""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.25):
         super().__init__(daemon=True)
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.period, self.samples, self.stop_flag, self.max_mhz = index, period, [], False, None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                parts = [p.strip() for p in line.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((mhz, mask))
+                time.sleep(self.period)
         except Exception:
             pass
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()     # the exact PID we started
+        self.stop_flag = True
         self.join(timeout=3)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mhz = sorted(int(float(s[0])) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(mhz)}
+        mhz = sorted(s[0] for s in self.samples)
+        reasons = [n for n, bit in self.REASONS.items() if any(s[1] & bit for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(mhz)}
 
 
 def peaks():
@@ -203,7 +208,7 @@ def time_gemm_kernels(c, rows, device, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
@@ -263,16 +268,18 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
     if sampler:
         sampler.start()
-        time.sleep(0.15)          # let nvidia-smi attach before the timed region starts
+        time.sleep(0.1)           # first NVML sample lands before the timed region starts
     launches0 = L.lib.svae_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for i in range(args.steps):
         res = device_step(i)
+        if os.environ.get("BENCH_SYNC_EACH"):
+            torch.cuda.synchronize()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
