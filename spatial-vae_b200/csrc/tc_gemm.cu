@@ -1,13 +1,16 @@
 // bf16 tensor-core GEMMs for the decoder hidden layers (models.py:82,126 and their backward) on
-// sm_100a: TMA (cp.async.bulk.tensor) feeds a 4-stage shared-memory ring, one elected thread issues
+// sm_100a: TMA (cp.async.bulk.tensor) feeds a shared-memory ring, one elected thread issues
 // tcgen05.mma with the fp32 accumulator in TMEM (two 128x256 accumulator stages = all 512 columns),
 // four epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue while the next tile's
-// MMAs run.  Persistent CTAs, one per SM.
+// MMAs run.  Persistent CTAs, one per SM.  CG = 2 pairs two SMs (cta_group::2, cluster of 2): the pair
+// computes a 256 x 256 tile, each CTA stages its own 128 A rows and HALF of the B tile, so the weight /
+// operand traffic through L2 and shared memory per FLOP halves (the 1-CTA kernel is L2-bandwidth bound).
 //
 //   mode 0  FWD : out[M,N]  = act(A[M,K] W[N,K]^T + bias)              A K-major,  B K-major
 //   mode 1  DX  : out[M,N]  = (A[M,K] W[K,N]) .* act'(aux[M,N])        A K-major,  B MN-major
 //   mode 2  DW  : outf[M,N] += A[Kr,M]^T Bm[Kr,N]  (split over Kr)     A MN-major, B MN-major
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -17,20 +20,22 @@ namespace svae {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 3;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 rows (or 128 M-columns) x 64 K
 constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64x64 bf16 TMA box (MN-major operands)
+__host__ __device__ constexpr int stages_of(int cg) { return cg == 2 ? 4 : 3; }
+__host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }     // 32 KB | 16 KB
+__host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
 constexpr int MAX_BIAS = 1024;                // widest hidden layer the epilogue tables hold
 constexpr int MAX_DOT_C = 3;                  // output channels the fused output-layer dot supports
 constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 64-column bf16 epilogue block (SWIZZLE_128B)
-constexpr int OFF_OUT_STAGE = STAGES * STAGE_BYTES;                 // 2 blocks: bf16 output staging for TMA stores
-constexpr int OFF_AUX_STAGE = OFF_OUT_STAGE + 2 * EPI_BLOCK_BYTES;  // 2 blocks: act[l-1] tiles for the dX epilogue
-constexpr int OFF_BIAS = OFF_AUX_STAGE + 2 * EPI_BLOCK_BYTES;
-constexpr int OFF_WO = OFF_BIAS + MAX_BIAS * 4;
-constexpr int OFF_BARS = OFF_WO + MAX_DOT_C * MAX_BIAS * 4;
-constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;                   // + barriers + 1 KB alignment slack
+// shared-memory map (after the operand ring): 2 output staging blocks, 2 aux blocks, bias, W_o, barriers
+__host__ __device__ constexpr int off_out_stage(int cg) { return stages_of(cg) * stage_bytes(cg); }
+__host__ __device__ constexpr int off_aux_stage(int cg) { return off_out_stage(cg) + 2 * EPI_BLOCK_BYTES; }
+__host__ __device__ constexpr int off_bias(int cg) { return off_aux_stage(cg) + 2 * EPI_BLOCK_BYTES; }
+__host__ __device__ constexpr int off_wo(int cg) { return off_bias(cg) + MAX_BIAS * 4; }
+__host__ __device__ constexpr int off_bars(int cg) { return off_wo(cg) + MAX_DOT_C * MAX_BIAS * 4; }
+__host__ __device__ constexpr int smem_bytes(int cg) { return off_bars(cg) + 256 + 1024; }   // + barriers + align slack
+static_assert(smem_bytes(1) <= 232448 && smem_bytes(2) <= 232448, "shared memory budget");
 constexpr int NUM_THREADS = 256;
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
 
@@ -85,6 +90,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes land on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// arrive (once the pair's MMAs retire) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -168,25 +217,37 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // MODE: 0 fwd, 1 dX, 2 dW.  ACT: activation of the epilogue (compile time so the per-element code
 // is branch free).  DOTC: output channels of the fused output-layer dot product (mode 0), 0 = none.
-template <int MODE, int ACT, int DOTC>
+// CG: 1 = one CTA per 128 x 256 tile; 2 = CTA pair (cluster of 2, cta_group::2) per 256 x 256 tile.
+template <int MODE, int ACT, int DOTC, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
+    constexpr int STAGES = stages_of(CG);
+    constexpr int B_STAGE_BYTES = b_stage_bytes(CG);
+    constexpr int STAGE_BYTES = stage_bytes(CG);
+    constexpr int BN_CTA = BN / CG;                // B-tile rows (N) staged by this CTA
+    constexpr int TILE_M = BM * CG;                // rows of the output tile computed by the CTA (pair)
+
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for SWIZZLE_128B tiles
+    // 1024-byte alignment for SWIZZLE_128B tiles (same offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-    float* s_wo = reinterpret_cast<float*>(smem + OFF_WO);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    float* s_bias = reinterpret_cast<float*>(smem + off_bias(CG));
+    float* s_wo = reinterpret_cast<float*>(smem + off_wo(CG));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars(CG));
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux_full[2], then the tmem base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader_cta = (cta_rank == 0);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
     const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
     const uint32_t auxfull0 = smem_u32(bars + 2 * STAGES + 4);
+    // barriers that live in the leader CTA of a pair (operand "full", accumulator "empty")
+    const uint32_t full0_leader = (CG == 2) ? map_to_cta(full0, 0) : full0;
+    const uint32_t tempty0_leader = (CG == 2) ? map_to_cta(tempty0, 0) : tempty0;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -194,10 +255,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (MODE != 2) tma_prefetch_desc(&tmOut);
         if (MODE == 1) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); mbar_init(auxfull0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4 * CG);         // 4 epilogue warps per CTA of the pair
+            mbar_init(auxfull0 + 8 * i, 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512);
+    }
     constexpr bool fuse_dot = (MODE == 0) && (DOTC > 0);
     if (MODE == 0) {
         for (int i = threadIdx.x; i < MAX_BIAS; i += NUM_THREADS)
@@ -211,47 +278,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) { __syncwarp(); cluster_sync_all(); }   // peer barriers initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+    const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA: its own A rows and its share of B) =====
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
             const int ks = tile / (p.m_tiles * p.n_tiles);
             const int mn = tile % (p.m_tiles * p.n_tiles);
             const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
             const int kb0 = ks * p.k_blocks_per_split;
             const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
+            const int a0 = mt * TILE_M + (int)cta_rank * BM;          // first A row / M column of this CTA
+            const int b0 = nt * BN + (int)cta_rank * BN_CTA;          // first B row / N column of this CTA
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                const uint32_t fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, STAGE_BYTES);
+                const uint32_t fb = full0_leader + 8 * stage;
+                if (is_leader_cta) mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES * CG);
                 const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                 const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+                auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+                    if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
+                };
                 if (MODE == 2) {
 #pragma unroll
-                    for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * BOX_BYTES, &tmA, fb, mt * BM + i * 64, kb * BK);
+                    for (int i = 0; i < BM / 64; ++i) load(sa + i * BOX_BYTES, &tmA, a0 + i * 64, kb * BK);
                 } else {
-                    tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
+                    load(sa, &tmA, kb * BK, a0);
                 }
                 if (MODE == 0) {
-                    tma_load_2d(sb, &tmB, fb, kb * BK, nt * BN);
+                    load(sb, &tmB, kb * BK, b0);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * BOX_BYTES, &tmB, fb, nt * BN + i * 64, kb * BK);
+                    for (int i = 0; i < BN_CTA / 64; ++i) load(sb + i * BOX_BYTES, &tmB, b0 + i * 64, kb * BK);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc(MODE == 2 ? 1 : 0, MODE == 0 ? 0 : 1, BM, BN);
+    } else if (warp == 1 && lane == 0 && is_leader_cta) {
+        // ===== MMA issuer (leader CTA of the pair) =====
+        constexpr uint32_t idesc = make_idesc(MODE == 2 ? 1 : 0, MODE == 0 ? 0 : 1, TILE_M, BN);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
             const int ks = tile / (p.m_tiles * p.n_tiles);
             const int kb0 = ks * p.k_blocks_per_split;
             const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
@@ -271,10 +345,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                     : make_smem_desc(sa + k * 32, 0, 1024);
                     const uint64_t bd = (MODE == 0) ? make_smem_desc(sb + k * 32, 0, 1024)
                                                     : make_smem_desc(sb + k * 2048, BOX_BYTES, 1024);
-                    umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                    if (CG == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, accum); else umma_bf16(d_tmem, ad, bd, idesc, accum);
                 }
-                umma_commit(empty0 + 8 * stage);                 // frees the smem slot once the MMAs retire
-                if (kb == kb1 - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+                // frees the smem slot (in both CTAs) once the MMAs retire; last K block: accumulator complete
+                if (CG == 2) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
+                if (kb == kb1 - 1) { if (CG == 2) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc); }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -282,14 +358,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (swizzled smem -> TMA store | fp32 reductions) =====
         const int q = warp & 3;                // TMEM lane quadrant of this warp
-        const int row = q * 32 + lane;         // row of the 128-row tile owned by this thread
+        const int row = q * 32 + lane;         // row of this CTA's 128-row slab owned by this thread
         const bool leader = (warp == 4 && lane == 0);
         int acc = 0; uint32_t acc_phase = 0;
+        auto release_accumulator = [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(tempty0_leader + 8 * acc); else mbar_arrive(tempty0 + 8 * acc);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        };
         if (MODE == 2) {
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
-                const int m = mt * BM + row;
+                const int m = mt * TILE_M + (int)cta_rank * BM + row;
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -315,19 +399,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                release_accumulator();
             }
         } else {
             // 64-column blocks: registers -> swizzled staging block -> one TMA store per block.
             // dX additionally streams the matching act[l-1] block in by TMA, two blocks ahead.
-            uint8_t* out_stage = smem + OFF_OUT_STAGE;
-            uint8_t* aux_stage = smem + OFF_AUX_STAGE;
+            uint8_t* out_stage = smem + off_out_stage(CG);
+            uint8_t* aux_stage = smem + off_aux_stage(CG);
             uint32_t blk = 0;                              // running block counter (staging buffer = blk & 1)
-            // prefetch cursor for the aux blocks (leader only)
-            int pf_tile = blockIdx.x, pf_jb = 0; uint32_t pf_blk = 0;
+            // prefetch cursor for the aux blocks (leader thread only)
+            int pf_tile = first_tile, pf_jb = 0; uint32_t pf_blk = 0;
             auto blocks_in_tile = [&](int tile) {
                 const int nt = (tile % (p.m_tiles * p.n_tiles)) % p.n_tiles;
                 const int left = (p.N - nt * BN) / 64;
@@ -339,15 +420,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
                 const uint32_t bar = auxfull0 + 8 * (pf_blk & 1);
                 mbar_expect_tx(bar, EPI_BLOCK_BYTES);
-                tma_load_2d(smem_u32(aux_stage + (pf_blk & 1) * EPI_BLOCK_BYTES), &tmAux, bar, nt * BN + pf_jb * 64, mt * BM);
+                tma_load_2d(smem_u32(aux_stage + (pf_blk & 1) * EPI_BLOCK_BYTES), &tmAux, bar, nt * BN + pf_jb * 64,
+                            mt * TILE_M + (int)cta_rank * BM);
                 ++pf_blk;
-                if (++pf_jb == blocks_in_tile(pf_tile)) { pf_jb = 0; pf_tile += gridDim.x; }
+                if (++pf_jb == blocks_in_tile(pf_tile)) { pf_jb = 0; pf_tile += tile_stride; }
             };
             if (MODE == 1 && leader) { prefetch_aux(); prefetch_aux(); }
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
-                const int m = mt * BM + row;
+                const int m_cta = mt * TILE_M + (int)cta_rank * BM;
+                const int m = m_cta + row;
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -414,15 +497,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();           // generic-proxy smem writes -> visible to the TMA (async proxy)
                     epi_bar_sync();
                     if (leader) {
-                        tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * 64, mt * BM);   // clips rows >= M
+                        tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * 64, m_cta);   // clips rows >= M
                         tma_store_commit();
                         if (MODE == 1) prefetch_aux();     // aux buffer `buf` is free again
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                release_accumulator();
                 if (fuse_dot && m < p.M) {
 #pragma unroll
                     for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot[c]);
@@ -434,9 +514,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) { __syncwarp(); cluster_sync_all(); }   // the peer may still be reading our operands / barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -477,41 +558,70 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
     return SVAE_OK;
 }
 
-template <int MODE, int ACT, int DOTC>
+template <int MODE, int ACT, int DOTC, int CG>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x, const TcParams& p,
            int grid, cudaStream_t st) {
     static bool configured = false;
+    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG>;
     if (!configured) {
-        SVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE, ACT, DOTC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES));
+        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG)));
         configured = true;
     }
-    tc_gemm_kernel<MODE, ACT, DOTC><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(a, b, o, x, p);
-    SVAE_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes(CG);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    SVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, o, x, p));
     return SVAE_OK;
+}
+
+template <int MODE, int ACT, int DOTC>
+int launch_cg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
+              const TcParams& p, int cg, int grid, cudaStream_t st) {
+    if (cg == 2) return launch<MODE, ACT, DOTC, 2>(a, b, o, x, p, grid, st);
+    return launch<MODE, ACT, DOTC, 1>(a, b, o, x, p, grid, st);
 }
 
 template <int MODE, int ACT>
 int launch_dot(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
-               const TcParams& p, int grid, cudaStream_t st) {
-    if (MODE != 0 || p.o_accum == nullptr) return launch<MODE, ACT, 0>(a, b, o, x, p, grid, st);
+               const TcParams& p, int cg, int grid, cudaStream_t st) {
+    if (MODE != 0 || p.o_accum == nullptr) return launch_cg<MODE, ACT, 0>(a, b, o, x, p, cg, grid, st);
     switch (p.dot_c) {
-        case 1: return launch<0, ACT, 1>(a, b, o, x, p, grid, st);
-        case 2: return launch<0, ACT, 2>(a, b, o, x, p, grid, st);
-        default: return launch<0, ACT, 3>(a, b, o, x, p, grid, st);
+        case 1: return launch_cg<0, ACT, 1>(a, b, o, x, p, cg, grid, st);
+        case 2: return launch_cg<0, ACT, 2>(a, b, o, x, p, cg, grid, st);
+        default: return launch_cg<0, ACT, 3>(a, b, o, x, p, cg, grid, st);
     }
 }
 
 template <int MODE>
 int launch_act(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
-               const TcParams& p, int grid, cudaStream_t st) {
+               const TcParams& p, int cg, int grid, cudaStream_t st) {
     switch (p.act) {
-        case SVAE_ACT_TANH: return launch_dot<MODE, SVAE_ACT_TANH>(a, b, o, x, p, grid, st);
-        case SVAE_ACT_LEAKYRELU: return launch_dot<MODE, SVAE_ACT_LEAKYRELU>(a, b, o, x, p, grid, st);
-        case SVAE_ACT_RELU: return launch_dot<MODE, SVAE_ACT_RELU>(a, b, o, x, p, grid, st);
-        case SVAE_ACT_SIGMOID: return launch_dot<MODE, SVAE_ACT_SIGMOID>(a, b, o, x, p, grid, st);
+        case SVAE_ACT_TANH: return launch_dot<MODE, SVAE_ACT_TANH>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_LEAKYRELU: return launch_dot<MODE, SVAE_ACT_LEAKYRELU>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_RELU: return launch_dot<MODE, SVAE_ACT_RELU>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_SIGMOID: return launch_dot<MODE, SVAE_ACT_SIGMOID>(a, b, o, x, p, cg, grid, st);
         default: set_error("tc_gemm: unknown activation %d", p.act); return SVAE_EINVAL;
     }
+}
+
+// CTA pairs by default; SVAE_TC_CTA_GROUP=1 selects the single-CTA kernel (A/B comparison, debugging)
+int cta_group_size() {
+    static int cg = 0;
+    if (cg == 0) {
+        const char* e = getenv("SVAE_TC_CTA_GROUP");
+        cg = (e != nullptr && e[0] == '1') ? 1 : 2;
+    }
+    return cg;
 }
 
 int sm_count() {
@@ -536,7 +646,8 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_n = bias_n; p.aux = reinterpret_cast<const __nv_bfloat16*>(aux); p.ldaux = ldaux;
     p.act = act; p.out = out; p.ldo = ldo;
-    p.m_tiles = ceil_div(M, BM);
+    const int cg = cta_group_size();
+    p.m_tiles = ceil_div(M, BM * cg);
     p.n_tiles = ceil_div(N, BN);
     p.k_blocks = ceil_div(K, BK);
     p.k_splits = 1;
@@ -552,7 +663,7 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
         SVAE_REQUIRE(o_accum == nullptr || (mode == 0 && dot_c >= 1 && dot_c <= MAX_DOT_C && out_w != nullptr),
                      SVAE_EINVAL, "tc_gemm fwd: fused output dot supports 1..%d channels", MAX_DOT_C);
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
-        SVAE_TRY(make_map(&mb, W, N, K, ldw, 64, 256));
+        SVAE_TRY(make_map(&mb, W, N, K, ldw, 64, 256 / cg));
         SVAE_TRY(make_map(&mo, out, M, N, ldo, 64, 128));
     } else if (mode == 1) {
         SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm dx: N, K must be multiples of 64");
@@ -566,7 +677,7 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
         SVAE_TRY(make_map(&ma, A, K, round_up(M, 64) <= lda ? round_up(M, 64) : lda, lda, 64, 64));
         SVAE_TRY(make_map(&mb, W, K, round_up(N, 64) <= ldw ? round_up(N, 64) : ldw, ldw, 64, 64));
         const int mn = p.m_tiles * p.n_tiles;
-        int splits = sms / mn;
+        int splits = (sms / cg) / mn;
         if (splits < 1) splits = 1;
         if (splits > p.k_blocks) splits = p.k_blocks;
         p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
@@ -574,10 +685,11 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
         p.vec_red = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     }
     const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
-    const int grid = tiles < sms ? tiles : sms;
-    if (mode == 0) return launch_act<0>(ma, mb, mo, mx, p, grid, st);
-    if (mode == 1) return launch_act<1>(ma, mb, mo, mx, p, grid, st);
-    return launch<2, SVAE_ACT_TANH, 0>(ma, mb, mo, mx, p, grid, st);
+    const int groups = sms / cg;                                   // CTAs (cg=1) or CTA pairs (cg=2) resident at once
+    const int grid = (tiles < groups ? tiles : groups) * cg;
+    if (mode == 0) return launch_act<0>(ma, mb, mo, mx, p, cg, grid, st);
+    if (mode == 1) return launch_act<1>(ma, mb, mo, mx, p, cg, grid, st);
+    return launch_cg<2, SVAE_ACT_TANH, 0>(ma, mb, mo, mx, p, cg, grid, st);
 }
 
 }  // namespace svae
