@@ -33,6 +33,9 @@ struct Plan {
     // offsets (bytes)
     size_t enc_acts, zo, enc_scratch, lat, img, zs, hz, S, dz, g_zo, o, g_o, acts, delta, wbf16;
     size_t act_stride = 0, delta_stride = 0, w_stride = 0;
+    // encoder on tensor cores (FAST): leading dimension of the fp32 activations and the bf16 split buffers
+    int enc_ld = 0;
+    size_t xs_k, gs_r, as_r, ws_k[SVAE_MAX_LAYERS], ws_r[SVAE_MAX_LAYERS];
 };
 
 static size_t take(size_t& cur, size_t bytes) {
@@ -81,10 +84,24 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.chunk = chunk;
     const size_t B = (size_t)(s.B > 0 ? s.B : 1), I = (size_t)s.I, rows = (size_t)chunk * s.P;
     size_t cur = 0;
-    p.enc_acts = take(cur, (size_t)s.Lq * B * s.Hq * 4);
+    const size_t Hqp = (size_t)round_up(s.Hq, 64);
+    p.enc_ld = fast ? (int)Hqp : s.Hq;
+    p.enc_acts = take(cur, (size_t)s.Lq * B * p.enc_ld * 4);
     p.zo = take(cur, B * 2 * I * 4);
-    const size_t wide = (size_t)(s.Hq > 2 * s.I ? s.Hq : 2 * s.I);
+    const size_t wide = (size_t)((size_t)p.enc_ld > 2 * I ? (size_t)p.enc_ld : 2 * I);
     p.enc_scratch = take(cur, 2 * B * wide * 4);
+    if (fast) {
+        const size_t kp0 = (size_t)round_up((long)s.P * s.Cin, 64);
+        const size_t kmax = kp0 > Hqp ? kp0 : Hqp;
+        p.xs_k = take(cur, B * 3 * kmax * 2);
+        p.gs_r = take(cur, 3 * B * Hqp * 2);
+        p.as_r = take(cur, 3 * B * kmax * 2);
+        for (int l = 0; l < s.Lq; ++l) {
+            const size_t kp = l == 0 ? kp0 : Hqp;
+            p.ws_k[l] = take(cur, Hqp * 3 * kp * 2);
+            p.ws_r[l] = take(cur, l == 0 ? 0 : 3 * Hqp * kp * 2);
+        }
+    }
     p.lat = take(cur, B * I * 4);
     p.img = take(cur, B * 4 * 4);
     p.zs = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
@@ -105,6 +122,18 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
 }
 
 // ---- encoder -------------------------------------------------------------------------------------
+// the 2I-wide head (models.py:41): small, stays on the fp32 FFMA kernel in both precisions
+static int encoder_head_forward(const SvaeShape& s, const SvaeEncoderParams& q, const float* h, long ld, float* out,
+                                cudaStream_t st) {
+    SgemmArgs a{};
+    a.A = h; a.sAm = ld; a.sAk = 1;
+    a.B = q.w[s.Lq]; a.sBk = 1; a.sBn = s.Hq;
+    a.C = out; a.ldc = 2 * s.I;
+    a.M = s.B; a.N = 2 * s.I; a.K = s.Hq;
+    a.bias = q.b[s.Lq];
+    return sgemm(a, st);
+}
+
 static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x, float* out,
                                 float* acts, cudaStream_t st) {
     const int n_in = s.P * s.Cin;
@@ -121,16 +150,87 @@ static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderPa
         SVAE_TRY(sgemm(a, st));
         cur = dst; k = s.Hq;
     }
-    SgemmArgs a{};
-    a.A = cur; a.sAm = k; a.sAk = 1;
-    a.B = q.w[s.Lq]; a.sBk = 1; a.sBn = k;
-    a.C = out; a.ldc = 2 * s.I;
-    a.M = s.B; a.N = 2 * s.I; a.K = k;
-    a.bias = q.b[s.Lq];
-    return sgemm(a, st);
+    return encoder_head_forward(s, q, cur, s.Hq, out, st);
+}
+
+// ---- encoder hidden layers on tensor cores (FAST): every fp32 GEMM = one bf16 tcgen05 GEMM over K' = 3K
+// built from hi/lo splits of both operands (split3), fp32 accumulate, fp32 output.
+struct EncTc {
+    const SvaeShape* s; const Plan* p; char* ws; cudaStream_t st;
+    int Hqp() const { return p->enc_ld; }
+    int kin(int l) const { return l == 0 ? s->P * s->Cin : s->Hq; }
+    int kinp(int l) const { return l == 0 ? (int)round_up((long)s->P * s->Cin, 64) : p->enc_ld; }
+    float* acts(int l) const { return reinterpret_cast<float*>(ws + p->enc_acts) + (size_t)l * s->B * p->enc_ld; }
+    __nv_bfloat16* b16(size_t off) const { return reinterpret_cast<__nv_bfloat16*>(ws + off); }
+};
+
+static int encoder_forward_tc(const EncTc& e, int act, const SvaeEncoderParams& q, const float* x, float* out) {
+    const SvaeShape& s = *e.s;
+    const float* cur = x;
+    long ld = e.kin(0);
+    for (int l = 0; l < s.Lq; ++l) {
+        const int k = e.kin(l), kp = e.kinp(l);
+        SVAE_TRY(split3(cur, s.B, k, ld, e.b16(e.p->xs_k), s.B, kp, 1, 0, e.st));
+        SVAE_TRY(split3(q.w[l], s.Hq, k, k, e.b16(e.p->ws_k[l]), e.Hqp(), kp, 1, 1, e.st));
+        TcExtra f32out;
+        f32out.out_f32 = 1;
+        SVAE_TRY(tc_gemm(0, s.B, e.Hqp(), 3 * kp, e.b16(e.p->xs_k), 3 * kp, e.b16(e.p->ws_k[l]), 3 * kp, q.b[l], s.Hq,
+                         nullptr, 0, act, e.acts(l), e.Hqp(), e.st, f32out));
+        cur = e.acts(l); ld = e.Hqp();
+    }
+    return encoder_head_forward(s, q, cur, ld, out, e.st);
 }
 
 // g_out (B,2I) is the gradient w.r.t. the head output; scratch holds two (B, max(Hq,2I)) buffers.
+static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams& q, const float* x,
+                               const float* g_out, SvaeEncoderParams& gq, float* scratch) {
+    const SvaeShape& s = *e.s;
+    const int Hqp = e.Hqp();
+    const size_t wide = (size_t)(Hqp > 2 * s.I ? Hqp : 2 * s.I);
+    float* buf[2] = {scratch, scratch + (size_t)s.B * wide};
+    // head (2I x Hq): fp32 FFMA
+    const float* a_top = e.acts(s.Lq - 1);
+    SgemmArgs w{};
+    w.A = g_out; w.sAm = 1; w.sAk = 2 * s.I;
+    w.B = a_top; w.sBk = Hqp; w.sBn = 1;
+    w.C = gq.w[s.Lq]; w.ldc = s.Hq;
+    w.M = 2 * s.I; w.N = s.Hq; w.K = s.B;
+    w.accumulate = 1; w.split_k = s.B >= 2048 ? 8 : (s.B >= 512 ? 4 : 1);
+    SVAE_TRY(sgemm(w, e.st));
+    SVAE_TRY(col_sum<float>(g_out, s.B, 2 * s.I, 2 * s.I, gq.b[s.Lq], e.st));
+    SgemmArgs d{};
+    d.A = g_out; d.sAm = 2 * s.I; d.sAk = 1;
+    d.B = q.w[s.Lq]; d.sBk = s.Hq; d.sBn = 1;
+    d.C = buf[0]; d.ldc = Hqp;
+    d.M = s.B; d.N = s.Hq; d.K = 2 * s.I;
+    d.dsrc = a_top; d.ld_dsrc = Hqp; d.dact = act;
+    SVAE_TRY(sgemm(d, e.st));
+    const float* g = buf[0];
+    int cur = 0;
+    for (int l = s.Lq - 1; l >= 0; --l) {
+        const float* a_in = (l == 0) ? x : e.acts(l - 1);
+        const int k_in = e.kin(l), kinp = e.kinp(l);
+        const long ld_in = (l == 0) ? k_in : Hqp;
+        // dW_l (Hq, k_in) += g^T a_in : terms stacked along the reduction dimension (rows)
+        SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->gs_r), s.B, Hqp, 0, 0, e.st));
+        SVAE_TRY(split3(a_in, s.B, k_in, ld_in, e.b16(e.p->as_r), s.B, kinp, 0, 1, e.st));
+        SVAE_TRY(tc_gemm(2, s.Hq, k_in, 3 * s.B, e.b16(e.p->gs_r), Hqp, e.b16(e.p->as_r), kinp, nullptr, 0, nullptr, 0, -1,
+                         gq.w[l], k_in, e.st));
+        SVAE_TRY(col_sum<float>(g, s.B, s.Hq, Hqp, gq.b[l], e.st));
+        if (l == 0) break;
+        // g_in (B, Hq) = (g W_l) .* act'(a_in)
+        SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->xs_k), s.B, Hqp, 1, 0, e.st));
+        SVAE_TRY(split3(q.w[l], s.Hq, k_in, k_in, e.b16(e.p->ws_r[l]), Hqp, kinp, 0, 1, e.st));
+        cur ^= 1;
+        TcExtra f32out;
+        f32out.out_f32 = 1;
+        SVAE_TRY(tc_gemm(1, s.B, kinp, 3 * Hqp, e.b16(e.p->xs_k), 3 * Hqp, e.b16(e.p->ws_r[l]), kinp, nullptr, 0, a_in,
+                         Hqp, act, buf[cur], Hqp, e.st, f32out));
+        g = buf[cur];
+    }
+    return SVAE_OK;
+}
+
 static int encoder_backward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x,
                                  const float* acts, const float* g_out, SvaeEncoderParams& gq, float* g_x,
                                  float* scratch, cudaStream_t st) {
@@ -200,17 +300,20 @@ int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Svae
                                   bool fuse_out) {
     const int Hp = d.p->Hp;
     if (fuse_out) SVAE_TRY(fill_rows(d.f(d.p->o), dp.out_b, rows, d.s->C, d.s->C, d.st));
+    TcExtra ex;
+    if (fuse_out) { ex.out_w = dp.out_w; ex.out_w_ld = d.s->H; ex.dot_c = d.s->C; ex.o_accum = d.f(d.p->o); }
     return tc_gemm(0, rows, Hp, Hp, d.act(l - 1), Hp, d.wbf(l - 1), Hp, dp.hidden_b[l - 1], d.s->H, nullptr, 0,
-                   d.c->activation, d.act(l), Hp, d.st, fuse_out ? dp.out_w : nullptr, d.s->H, fuse_out ? d.s->C : 0,
-                   fuse_out ? d.f(d.p->o) : nullptr);
+                   d.c->activation, d.act(l), Hp, d.st, ex);
 }
 
+// red: (FAST only) do not store delta_prev; reduce it per image into S on the fly (first layer's sums)
+struct RedSpec { float* S = nullptr; const float* grid = nullptr; int b0 = 0; };
 template <typename T>
 static int hidden_backward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l, int rows,
-                           const T* delta, T* delta_prev);
+                           const T* delta, T* delta_prev, const RedSpec& red);
 template <>
 int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l,
-                           int rows, const float* delta, float* delta_prev) {
+                           int rows, const float* delta, float* delta_prev, const RedSpec&) {
     const int H = d.s->H, Hp = d.p->Hp;
     // dW_l (H,H) += delta^T act[l-1]
     SgemmArgs w{};
@@ -234,13 +337,15 @@ int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& 
 template <>
 int hidden_backward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp,
                                    SvaeDecoderParams& g, int l, int rows, const __nv_bfloat16* delta,
-                                   __nv_bfloat16* delta_prev) {
+                                   __nv_bfloat16* delta_prev, const RedSpec& red) {
     const int H = d.s->H, Hp = d.p->Hp;
     (void)dp;
     // dW_l (H,H; ld H) += delta^T act[l-1]   (fp32 accumulate, atomics across row splits)
     SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
+    TcExtra ex;
+    if (red.S != nullptr) { ex.red_S = red.S; ex.red_ld = Hp; ex.red_grid = red.grid; ex.red_P = d.s->P; ex.red_b0 = red.b0; }
     return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
-                   delta_prev, Hp, d.st);
+                   delta_prev, Hp, d.st, ex);
 }
 
 // forward of the decoder over images [b0, b0+nb): fills act[0..L-1] and logits o; optional y_hat
@@ -273,12 +378,19 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     int cur = 0;
     SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.f(d.p->g_o), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
                              g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
+    // FAST, grid coordinates, P fits the int16 image table: the last dX GEMM reduces delta_0 per image in its
+    // epilogue (S must be zero on entry) instead of storing it and re-reading it in image_col_reduce.
+    const bool fuse_red = !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr && g_x == nullptr &&
+                          (long)s.B < 32000;
+    bool reduced = false;
     for (int l = s.L - 1; l >= 1; --l) {
-        SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1)));
+        RedSpec red;
+        if (fuse_red && l == 1) { red.S = d.f(d.p->S); red.grid = grid; red.b0 = b0; reduced = true; }
+        SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1), red));
         cur ^= 1;
         if (l - 1 >= 1) SVAE_TRY(col_sum<T>(d.delta(cur), rows, s.H, Hp, g.hidden_b[l - 2], d.st));
     }
-    SVAE_TRY(image_col_reduce<T>(d.delta(cur), b0, nb, s.P, Hp, grid, x_explicit, d.f(d.p->S), d.st));
+    if (!reduced) SVAE_TRY(image_col_reduce<T>(d.delta(cur), b0, nb, s.P, Hp, grid, x_explicit, d.f(d.p->S), d.st));
     if (g_x) SVAE_TRY(coord_row_grad<T>(d.delta(cur), rows, s.H, Hp, dp.coord_w, g_x + (size_t)b0 * s.P * 2, d.st));
     return SVAE_OK;
 }
@@ -352,11 +464,15 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     const bool train = (gd != nullptr);
     const float* x_enc = in.y_enc ? in.y_enc : in.y;
     float* zo = d.f(p.zo);
-    SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st));
+    constexpr bool kFast = !std::is_same<T, float>::value;
+    EncTc enc_tc{&s, &p, ws, st};
+    if (kFast) SVAE_TRY(encoder_forward_tc(enc_tc, c.activation, qp, x_enc, zo));
+    else SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st));
     float* lat = out.latent ? out.latent : d.f(p.lat);
     SVAE_TRY(latent_forward(s, c, zo, in.eps, in.theta_offset, lat, d.f(p.img), d.f(p.zs), out.stats, st));
     SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
+    if (train && kFast) SVAE_CUDA(cudaMemsetAsync(ws + p.S, 0, (size_t)s.B * 3 * p.Hp * sizeof(float), st));
     for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
         const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
         SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, in.grid, nullptr, out.y_hat));
@@ -370,8 +486,11 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
                                          s.Z > 0 ? d.f(p.dz) : nullptr, st));
         SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
                                  in.eps, d.f(p.g_zo), st));
-        if (gq) SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
-                                               d.f(p.enc_scratch), st));
+        if (gq) {
+            if (kFast) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));
+            else SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
+                                                d.f(p.enc_scratch), st));
+        }
     }
     return SVAE_OK;
 }

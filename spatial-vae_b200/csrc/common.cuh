@@ -98,8 +98,16 @@ struct SgemmArgs {
 int sgemm(const SgemmArgs& a, cudaStream_t st);
 
 // ---- bf16 tcgen05 GEMMs (tc_gemm.cu) -----------------------------------------------------------
+struct TcExtra {
+    // mode 0: fused output-layer dot product  o_accum[m,c] += sum_n h[m,n] out_w[c,n]
+    const float* out_w = nullptr; int out_w_ld = 0; int dot_c = 0; float* o_accum = nullptr;
+    // modes 0/1: fp32 output (and fp32 aux) instead of bf16
+    int out_f32 = 0;
+    // mode 1: per-image moments S[b0 + m/P, {1,x,y}, n] += out[m,n] * {1, grid[m%P]} instead of storing out
+    float* red_S = nullptr; int red_ld = 0; const float* red_grid = nullptr; int red_P = 0; int red_b0 = 0;
+};
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
             int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
-            const float* out_w = nullptr, int out_w_ld = 0, int dot_c = 0, float* o_accum = nullptr);
+            const TcExtra& ex = TcExtra());
 
 }  // namespace svae

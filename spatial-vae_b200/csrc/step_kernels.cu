@@ -849,4 +849,36 @@ int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int
     return SVAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 -> three bf16 terms for error-compensated tensor-core GEMMs (encoder):
+//   x = hi + lo (+ 2^-17 |x|),  A*B ~ Ahi*Bhi + Ahi*Blo + Alo*Bhi
+// pattern 0 ("A side") emits (hi, hi, lo), pattern 1 ("B side") emits (hi, lo, hi); the three terms are laid
+// side by side along K: kcat = 1 -> dst (rows_p, 3*cols_p) with term t at columns [t*cols_p, ...),
+// kcat = 0 -> dst (3*rows_p, cols_p) with term t at rows [t*rows_p, ...).  Padding is written as zeros.
+// ------------------------------------------------------------------------------------------------
+__global__ void split3_k(const float* __restrict__ src, int rows, int cols, long ld, __nv_bfloat16* __restrict__ dst,
+                         int rows_p, int cols_p, int kcat, int pattern) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows_p * cols_p) return;
+    const int r = (int)(i / cols_p), c = (int)(i % cols_p);
+    const float x = (r < rows && c < cols) ? src[(long)r * ld + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const __nv_bfloat16 t1 = pattern == 0 ? hi : lo, t2 = pattern == 0 ? lo : hi;
+    if (kcat) {
+        __nv_bfloat16* d = dst + (long)r * 3 * cols_p + c;
+        d[0] = hi; d[cols_p] = t1; d[2 * cols_p] = t2;
+    } else {
+        __nv_bfloat16* d = dst + (long)r * cols_p + c;
+        const long seg = (long)rows_p * cols_p;
+        d[0] = hi; d[seg] = t1; d[2 * seg] = t2;
+    }
+}
+int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, int rows_p, int cols_p, int kcat,
+           int pattern, cudaStream_t st) {
+    split3_k<<<ceil_div((long)rows_p * cols_p, 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat, pattern);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
 }  // namespace svae

@@ -1,13 +1,16 @@
 // bf16 tensor-core GEMMs for the decoder hidden layers (models.py:82,126 and their backward) on
 // sm_100a: TMA (cp.async.bulk.tensor) feeds a shared-memory ring, one elected thread issues
 // tcgen05.mma with the fp32 accumulator in TMEM (two 128x256 accumulator stages = all 512 columns),
-// four epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue while the next tile's
+// epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue while the next tile's
 // MMAs run.  Persistent CTAs, one per SM.  CG = 2 pairs two SMs (cta_group::2, cluster of 2): the pair
 // computes a 256 x 256 tile, each CTA stages its own 128 A rows and HALF of the B tile, so the weight /
-// operand traffic through L2 and shared memory per FLOP halves (the 1-CTA kernel is L2-bandwidth bound).
+// operand traffic through L2 and shared memory per FLOP halves; the pair kernel also runs TWO epilogue
+// warp-groups (one warp per scheduler was latency bound: ncu showed 23 % issue utilisation).
 //
 //   mode 0  FWD : out[M,N]  = act(A[M,K] W[N,K]^T + bias)              A K-major,  B K-major
+//                 (+ optional fused output layer: o[m,c] += sum_n h[m,n] W_o[c,n])
 //   mode 1  DX  : out[M,N]  = (A[M,K] W[K,N]) .* act'(aux[M,N])        A K-major,  B MN-major
+//                 (RED: instead of storing, reduce per image: S[b,{1,x,y},n] += sum_p out[b*P+p, n] {1,x_p,y_p})
 //   mode 2  DW  : outf[M,N] += A[Kr,M]^T Bm[Kr,N]  (split over Kr)     A MN-major, B MN-major
 #include <cuda.h>
 #include <stdlib.h>
@@ -22,21 +25,35 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 rows (or 128 M-columns) x 64 K
 constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64x64 bf16 TMA box (MN-major operands)
-__host__ __device__ constexpr int stages_of(int cg) { return cg == 2 ? 4 : 3; }
-__host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }     // 32 KB | 16 KB
-__host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
-constexpr int MAX_BIAS = 1024;                // widest hidden layer the epilogue tables hold
 constexpr int MAX_DOT_C = 3;                  // output channels the fused output-layer dot supports
-constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 64-column bf16 epilogue block (SWIZZLE_128B)
-// shared-memory map (after the operand ring): 2 output staging blocks, 2 aux blocks, bias, W_o, barriers
-__host__ __device__ constexpr int off_out_stage(int cg) { return stages_of(cg) * stage_bytes(cg); }
-__host__ __device__ constexpr int off_aux_stage(int cg) { return off_out_stage(cg) + 2 * EPI_BLOCK_BYTES; }
-__host__ __device__ constexpr int off_bias(int cg) { return off_aux_stage(cg) + 2 * EPI_BLOCK_BYTES; }
-__host__ __device__ constexpr int off_wo(int cg) { return off_bias(cg) + MAX_BIAS * 4; }
-__host__ __device__ constexpr int off_bars(int cg) { return off_wo(cg) + MAX_DOT_C * MAX_BIAS * 4; }
-__host__ __device__ constexpr int smem_bytes(int cg) { return off_bars(cg) + 256 + 1024; }   // + barriers + align slack
-static_assert(smem_bytes(1) <= 232448 && smem_bytes(2) <= 232448, "shared memory budget");
-constexpr int NUM_THREADS = 256;
+constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 128-byte epilogue block (SWIZZLE_128B)
+__host__ __device__ constexpr int epi_groups(int cg) { return cg == 2 ? 2 : 1; }             // epilogue warp-groups
+__host__ __device__ constexpr int num_threads(int cg) { return 128 + 128 * epi_groups(cg); }
+__host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }        // 32 KB | 16 KB
+__host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
+// ring depth: whatever the staging blocks leave (mode 1 needs aux blocks too)
+__host__ __device__ constexpr int stages_of(int cg, int mode) { return cg == 2 ? (mode == 1 ? 3 : 4) : 3; }
+// shared-memory map after the operand ring:
+//   2 output staging blocks per epilogue group | (mode 1) 2 aux blocks per group |
+//   tables: mode 0: 2 x (bias[BN] + W_o[3][BN]) floats; mode 1 RED: 2 x (x[128], y[128], image[128]) | barriers
+__host__ __device__ constexpr int off_out_stage(int cg, int mode) { return stages_of(cg, mode) * stage_bytes(cg); }
+__host__ __device__ constexpr int off_aux_stage(int cg, int mode) {
+    return off_out_stage(cg, mode) + (mode == 2 ? 0 : 2 * epi_groups(cg) * EPI_BLOCK_BYTES);
+}
+__host__ __device__ constexpr int off_tables(int cg, int mode) {
+    return off_aux_stage(cg, mode) + (mode == 1 ? 2 * epi_groups(cg) * EPI_BLOCK_BYTES : 0);
+}
+constexpr int RED_TABLE_BYTES = 128 * 8 + 128 * 2;    // (x,y) float2 per row + int16 image index per row
+__host__ __device__ constexpr int table_bytes(int mode) {
+    return mode == 0 ? 2 * (1 + MAX_DOT_C) * BN * 4 : (mode == 1 ? 2 * RED_TABLE_BYTES : 0);
+}
+__host__ __device__ constexpr int off_bars(int cg, int mode) { return off_tables(cg, mode) + table_bytes(mode); }
+// The dynamic shared memory is declared 1024-byte aligned; the pair dX kernel has no room for alignment slack
+// (it traps if the base ever comes back misaligned), the others keep 1 KB of slack and align by hand.
+__host__ __device__ constexpr int align_slack(int cg, int mode) { return (cg == 2 && mode == 1) ? 0 : 1024; }
+__host__ __device__ constexpr int smem_bytes(int cg, int mode) { return off_bars(cg, mode) + 256 + align_slack(cg, mode); }
+static_assert(smem_bytes(1, 0) <= 232448 && smem_bytes(1, 1) <= 232448 && smem_bytes(2, 0) <= 232448 &&
+              smem_bytes(2, 1) <= 232448 && smem_bytes(2, 2) <= 232448, "shared memory budget");
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
@@ -47,8 +64,11 @@ struct TcParams {
     int act;
     void* out; int ldo;
     int vec_red;              // mode 2: 16-byte aligned rows -> red.global.add.v4.f32
+    int out_f32;              // modes 0/1: fp32 output (and fp32 aux) instead of bf16
     // mode 0, optional: fused output layer (models.py:84): o_accum[m, c] += sum_n h[m,n] * out_w[c, n]
     const float* out_w; int out_w_ld; int dot_c; float* o_accum;
+    // mode 1 RED: per-image moments of the result instead of storing it
+    float* red_S; int red_ld; const float* red_grid; int red_P; int red_b0;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -142,7 +162,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barriers of the epilogue: id 1+g = the 128 threads of warp-group g, id 3 = all epilogue threads
+__device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync_all(int nthreads) { asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -218,26 +240,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // MODE: 0 fwd, 1 dX, 2 dW.  ACT: activation of the epilogue (compile time so the per-element code
 // is branch free).  DOTC: output channels of the fused output-layer dot product (mode 0), 0 = none.
 // CG: 1 = one CTA per 128 x 256 tile; 2 = CTA pair (cluster of 2, cta_group::2) per 256 x 256 tile.
-template <int MODE, int ACT, int DOTC, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// OUT32: modes 0/1 write fp32 (and read an fp32 aux matrix) instead of bf16: used by the encoder, whose
+// fp32 GEMMs run as three bf16 MMAs on hi/lo splits of the operands (error-compensated, ~fp32 accuracy).
+// RED: mode 1 only: per-image column moments of the result instead of storing it.
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED>
+__global__ void __launch_bounds__(num_threads(CG), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
-    constexpr int STAGES = stages_of(CG);
+    constexpr int STAGES = stages_of(CG, MODE);
     constexpr int B_STAGE_BYTES = b_stage_bytes(CG);
     constexpr int STAGE_BYTES = stage_bytes(CG);
     constexpr int BN_CTA = BN / CG;                // B-tile rows (N) staged by this CTA
     constexpr int TILE_M = BM * CG;                // rows of the output tile computed by the CTA (pair)
+    constexpr int EG = epi_groups(CG);             // epilogue warp-groups (4 warps each)
+    constexpr int NT = num_threads(CG);
 
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles (same offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if (align_slack(CG, MODE) == 0 && smem != smem_raw) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    float* s_bias = reinterpret_cast<float*>(smem + off_bias(CG));
-    float* s_wo = reinterpret_cast<float*>(smem + off_wo(CG));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars(CG));
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux_full[2], then the tmem base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    float* s_tab = reinterpret_cast<float*>(smem + off_tables(CG, MODE));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars(CG, MODE));
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux_full[2*EG], then the tmem base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * EG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -252,30 +279,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (MODE != 2) tma_prefetch_desc(&tmOut);
+        if (MODE != 2 && !RED) tma_prefetch_desc(&tmOut);
         if (MODE == 1) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4 * CG);         // 4 epilogue warps per CTA of the pair
-            mbar_init(auxfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4 * EG * CG);    // every epilogue warp of the CTA (pair)
         }
+        for (int i = 0; i < 2 * EG; ++i) mbar_init(auxfull0 + 8 * i, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
         if (CG == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512);
     }
     constexpr bool fuse_dot = (MODE == 0) && (DOTC > 0);
-    if (MODE == 0) {
-        for (int i = threadIdx.x; i < MAX_BIAS; i += NUM_THREADS)
-            s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.f;
-        if (fuse_dot) {
-            for (int i = threadIdx.x; i < DOTC * MAX_BIAS; i += NUM_THREADS) {
-                const int c = i / MAX_BIAS, n = i % MAX_BIAS;
-                s_wo[i] = (n < p.bias_n) ? p.out_w[(size_t)c * p.out_w_ld + n] : 0.f;
-            }
-        }
-    }
     tc_fence_before();
     __syncthreads();
     if (CG == 2) { __syncwarp(); cluster_sync_all(); }   // peer barriers initialised before anyone signals them
@@ -356,10 +373,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> (swizzled smem -> TMA store | fp32 reductions) =====
+        // ===== epilogue: TMEM -> registers -> (swizzled smem -> TMA store | reductions) =====
+        const int eg = (warp - 4) >> 2;        // epilogue warp-group of this warp
         const int q = warp & 3;                // TMEM lane quadrant of this warp
         const int row = q * 32 + lane;         // row of this CTA's 128-row slab owned by this thread
-        const bool leader = (warp == 4 && lane == 0);
+        const int gtid = threadIdx.x - 128 - eg * 128;        // 0..127 within the group
+        const int etid = threadIdx.x - 128;                   // 0..128*EG-1 over all epilogue threads
+        const bool leader = (gtid == 0);
         int acc = 0; uint32_t acc_phase = 0;
         auto release_accumulator = [&]() {
             tc_fence_before();
@@ -370,6 +390,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         };
         if (MODE == 2) {
+            // fp32 partial dW tile -> global atomics; group g takes the 32-column chunks c/32 == g (mod EG)
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
@@ -378,7 +399,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = eg * 32; c < BN; c += 32 * EG) {
                     const int n = nt * BN + c;
                     if (n >= p.N) break;
                     uint32_t v[32];
@@ -402,35 +423,73 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 release_accumulator();
             }
         } else {
-            // 64-column blocks: registers -> swizzled staging block -> one TMA store per block.
-            // dX additionally streams the matching act[l-1] block in by TMA, two blocks ahead.
-            uint8_t* out_stage = smem + off_out_stage(CG);
-            uint8_t* aux_stage = smem + off_aux_stage(CG);
-            uint32_t blk = 0;                              // running block counter (staging buffer = blk & 1)
-            // prefetch cursor for the aux blocks (leader thread only)
-            int pf_tile = first_tile, pf_jb = 0; uint32_t pf_blk = 0;
+            // 128-byte-wide column blocks: registers -> swizzled staging block -> TMA store (or reduction).
+            // Group g takes blocks jb == g (mod EG) of every tile.  dX additionally streams the matching
+            // act[l-1] block in by TMA, two of the group's blocks ahead.
+            constexpr int BCOLS = OUT32 ? 32 : 64;         // columns per 128-byte-wide staging block
+            constexpr int HALVES = OUT32 ? 1 : 2;          // 32-column TMEM loads per block
+            uint8_t* out_stage = smem + off_out_stage(CG, MODE) + eg * 2 * EPI_BLOCK_BYTES;
+            uint8_t* aux_stage = smem + off_aux_stage(CG, MODE) + eg * 2 * EPI_BLOCK_BYTES;
+            const uint32_t auxfull_g = auxfull0 + 8 * (2 * eg);
+            uint32_t blk = 0;                              // this group's running block counter (buffer = blk & 1)
+            uint32_t tile_it = 0;                          // tiles processed (parity selects the table copy)
             auto blocks_in_tile = [&](int tile) {
                 const int nt = (tile % (p.m_tiles * p.n_tiles)) % p.n_tiles;
-                const int left = (p.N - nt * BN) / 64;
-                return left < BN / 64 ? left : BN / 64;
+                const int left = (p.N - nt * BN) / BCOLS;
+                return left < BN / BCOLS ? left : BN / BCOLS;
             };
+            // prefetch cursor over this group's aux blocks (leader thread of the group only)
+            int pf_tile = first_tile, pf_jb = eg; uint32_t pf_blk = 0;
             auto prefetch_aux = [&]() {
+                while (pf_tile < num_tiles && pf_jb >= blocks_in_tile(pf_tile)) { pf_jb = eg; pf_tile += tile_stride; }
                 if (pf_tile >= num_tiles) return;
                 const int mn = pf_tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
-                const uint32_t bar = auxfull0 + 8 * (pf_blk & 1);
+                const uint32_t bar = auxfull_g + 8 * (pf_blk & 1);
                 mbar_expect_tx(bar, EPI_BLOCK_BYTES);
-                tma_load_2d(smem_u32(aux_stage + (pf_blk & 1) * EPI_BLOCK_BYTES), &tmAux, bar, nt * BN + pf_jb * 64,
+                tma_load_2d(smem_u32(aux_stage + (pf_blk & 1) * EPI_BLOCK_BYTES), &tmAux, bar, nt * BN + pf_jb * BCOLS,
                             mt * TILE_M + (int)cta_rank * BM);
                 ++pf_blk;
-                if (++pf_jb == blocks_in_tile(pf_tile)) { pf_jb = 0; pf_tile += tile_stride; }
+                pf_jb += EG;
             };
             if (MODE == 1 && leader) { prefetch_aux(); prefetch_aux(); }
-            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++tile_it) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
                 const int m_cta = mt * TILE_M + (int)cta_rank * BM;
                 const int m = m_cta + row;
+                const int par = tile_it & 1;
+                // per-tile tables, double buffered by tile parity (a fast group may already be one tile ahead)
+                float* s_bias = s_tab + par * (1 + MAX_DOT_C) * BN;
+                float* s_wo = s_bias + BN;
+                float2* s_xy = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_tab) + par * RED_TABLE_BYTES);
+                short* s_img = reinterpret_cast<short*>(s_xy + 128);
+                if (MODE == 0) {
+                    for (int i = etid; i < BN; i += 128 * EG) {
+                        const int n = nt * BN + i;
+                        s_bias[i] = (p.bias != nullptr && n < p.bias_n) ? p.bias[n] : 0.f;
+                        if (fuse_dot) {
+#pragma unroll
+                            for (int c = 0; c < DOTC; ++c)
+                                s_wo[c * BN + i] = (n < p.bias_n) ? p.out_w[(size_t)c * p.out_w_ld + n] : 0.f;
+                        }
+                    }
+                    epi_bar_sync_all(128 * EG);
+                }
+                if (RED) {
+                    for (int i = etid; i < 128; i += 128 * EG) {
+                        const int mr = m_cta + i;
+                        int img = -1; float cx = 0.f, cy = 0.f;
+                        if (mr < p.M) {
+                            img = mr / p.red_P;
+                            const int pp = mr - img * p.red_P;
+                            cx = __ldg(p.red_grid + 2 * pp); cy = __ldg(p.red_grid + 2 * pp + 1);
+                            img += p.red_b0;
+                        }
+                        s_xy[i] = make_float2(cx, cy); s_img[i] = (short)img;
+                    }
+                    epi_bar_sync_all(128 * EG);
+                }
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -439,67 +498,123 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int c = 0; c < (DOTC > 0 ? DOTC : 1); ++c) dot[c] = 0.f;
 #pragma unroll 1
-                for (int jb = 0; jb < nblk; ++jb, ++blk) {
+                for (int jb = eg; jb < nblk; jb += EG, ++blk) {
                     const uint32_t buf = blk & 1;
                     uint8_t* ostage = out_stage + buf * EPI_BLOCK_BYTES;
                     const uint8_t* astage = aux_stage + buf * EPI_BLOCK_BYTES;
-                    if (MODE == 1) mbar_wait(auxfull0 + 8 * buf, (blk >> 1) & 1);
+                    if (MODE == 1) mbar_wait(auxfull_g + 8 * buf, (blk >> 1) & 1);
                     // the TMA store issued two blocks ago must have finished READING this staging buffer
-                    if (leader) tma_store_wait_read<1>();
-                    epi_bar_sync();
+                    if (!RED && leader) tma_store_wait_read<1>();
+                    epi_bar_sync(eg);
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int n = nt * BN + jb * 64 + half * 32;      // first column of this 32-wide chunk
+                    for (int half = 0; half < HALVES; ++half) {
+                        const int tc = jb * BCOLS + half * 32;             // first tile-local column of this chunk
                         uint32_t v[32];
-                        tmem_ld32(t_row + jb * 64 + half * 32, v);
-                        uint4 auxv[4];
-                        if (MODE == 1) {
+                        tmem_ld32(t_row + tc, v);
+                        if (OUT32) {
+                            // fp32 in / fp32 out: the block is 32 columns = 8 chunks of 4 floats
+                            uint4 auxv[8];
+                            if (MODE == 1) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                auxv[j] = *reinterpret_cast<const uint4*>(astage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4));
-                        }
-                        tmem_ld_wait();
-                        uint32_t packed[16];
-                        if (MODE == 0) {
+                                for (int j = 0; j < 8; ++j)
+                                    auxv[j] = *reinterpret_cast<const uint4*>(astage + row * 128 + ((j ^ (row & 7)) << 4));
+                            }
+                            tmem_ld_wait();
+                            const float* af = reinterpret_cast<const float*>(auxv);
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {          // 4 columns at a time: 128-bit table reads
-                                const float4 bv = *reinterpret_cast<const float4*>(s_bias + n + 4 * j4);
-                                const float hh[4] = {
-                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 0]) + bv.x),
-                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 1]) + bv.y),
-                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 2]) + bv.z),
-                                    act_const<ACT>(__uint_as_float(v[4 * j4 + 3]) + bv.w)};
-                                packed[2 * j4] = pack_bf16(hh[0], hh[1]);
-                                packed[2 * j4 + 1] = pack_bf16(hh[2], hh[3]);
-                                if (fuse_dot) {
+                            for (int j = 0; j < 8; ++j) {
+                                float r[4];
 #pragma unroll
-                                    for (int c = 0; c < DOTC; ++c) {
-                                        const float4 wv = *reinterpret_cast<const float4*>(s_wo + c * MAX_BIAS + n + 4 * j4);
-                                        dot[c] = fmaf(hh[0], wv.x, fmaf(hh[1], wv.y, fmaf(hh[2], wv.z, fmaf(hh[3], wv.w, dot[c]))));
-                                    }
+                                for (int e = 0; e < 4; ++e) {
+                                    const float x = __uint_as_float(v[4 * j + e]);
+                                    r[e] = (MODE == 0) ? act_const<ACT>(x + s_bias[tc + 4 * j + e])
+                                                       : x * act_deriv_const<ACT>(af[4 * j + e]);
                                 }
+                                *reinterpret_cast<float4*>(ostage + row * 128 + ((j ^ (row & 7)) << 4)) =
+                                    make_float4(r[0], r[1], r[2], r[3]);
                             }
                         } else {
-                            const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv);
+                            uint4 auxv[4];
+                            if (MODE == 1) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-                                const float d0 = __uint_as_float(v[2 * j]) * act_deriv_const<ACT>(__low2float(hv));
-                                const float d1 = __uint_as_float(v[2 * j + 1]) * act_deriv_const<ACT>(__high2float(hv));
-                                packed[j] = pack_bf16(d0, d1);
+                                for (int j = 0; j < 4; ++j)
+                                    auxv[j] = *reinterpret_cast<const uint4*>(astage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4));
                             }
-                        }
+                            tmem_ld_wait();
+                            uint32_t packed[16];
+                            if (MODE == 0) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(ostage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) =
-                                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                                for (int j4 = 0; j4 < 8; ++j4) {          // 4 columns at a time: 128-bit table reads
+                                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + tc + 4 * j4);
+                                    const float hh[4] = {
+                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 0]) + bv.x),
+                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 1]) + bv.y),
+                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 2]) + bv.z),
+                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 3]) + bv.w)};
+                                    packed[2 * j4] = pack_bf16(hh[0], hh[1]);
+                                    packed[2 * j4 + 1] = pack_bf16(hh[2], hh[3]);
+                                    if (fuse_dot) {
+#pragma unroll
+                                        for (int c = 0; c < DOTC; ++c) {
+                                            const float4 wv = *reinterpret_cast<const float4*>(s_wo + c * BN + tc + 4 * j4);
+                                            dot[c] = fmaf(hh[0], wv.x, fmaf(hh[1], wv.y, fmaf(hh[2], wv.z, fmaf(hh[3], wv.w, dot[c]))));
+                                        }
+                                    }
+                                }
+                            } else {
+                                const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+                                    const float d0 = __uint_as_float(v[2 * j]) * act_deriv_const<ACT>(__low2float(hv));
+                                    const float d1 = __uint_as_float(v[2 * j + 1]) * act_deriv_const<ACT>(__high2float(hv));
+                                    packed[j] = pack_bf16(d0, d1);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(ostage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) =
+                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
                     }
-                    fence_proxy_async();           // generic-proxy smem writes -> visible to the TMA (async proxy)
-                    epi_bar_sync();
+                    if (!RED) fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    epi_bar_sync(eg);
                     if (leader) {
-                        tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * 64, m_cta);   // clips rows >= M
-                        tma_store_commit();
+                        if (!RED) {
+                            tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * BCOLS, m_cta);   // clips rows >= M
+                            tma_store_commit();
+                        }
                         if (MODE == 1) prefetch_aux();     // aux buffer `buf` is free again
+                    }
+                    if (RED) {
+                        // per-image moments of this 128 x 64 bf16 block: thread = (column pair, 32-row quarter)
+                        const int cp = gtid & 31, rq = gtid >> 5;
+                        const int n = nt * BN + jb * 64 + 2 * cp;
+                        const uint8_t* colp = ostage + (cp & 3) * 4;
+                        float s0 = 0.f, s1 = 0.f, x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+                        int cur = -1;
+                        auto flush = [&]() {
+                            if (cur >= 0) {
+                                float* sp = p.red_S + (size_t)cur * 3 * p.red_ld + n;
+                                atomicAdd(sp, s0); atomicAdd(sp + 1, s1);
+                                atomicAdd(sp + p.red_ld, x0); atomicAdd(sp + p.red_ld + 1, x1);
+                                atomicAdd(sp + 2 * p.red_ld, y0); atomicAdd(sp + 2 * p.red_ld + 1, y1);
+                            }
+                            s0 = s1 = x0 = x1 = y0 = y1 = 0.f;
+                        };
+#pragma unroll 4
+                        for (int r = rq * 32; r < rq * 32 + 32; ++r) {
+                            const int img = s_img[r];
+                            if (img != cur) { flush(); cur = img; }
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r * 128 + (((cp >> 2) ^ (r & 7)) << 4));
+                            const float d0 = __uint_as_float(w << 16), d1 = __uint_as_float(w & 0xffff0000u);
+                            const float2 xy = s_xy[r];
+                            const float cx = xy.x, cy = xy.y;
+                            s0 += d0; s1 += d1;
+                            x0 = fmaf(cx, d0, x0); x1 = fmaf(cx, d1, x1);
+                            y0 = fmaf(cy, d0, y0); y1 = fmaf(cy, d1, y1);
+                        }
+                        flush();
                     }
                 }
                 release_accumulator();
@@ -508,7 +623,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot[c]);
                 }
             }
-            if (leader) tma_store_wait_read<0>();
+            if (!RED && leader) tma_store_wait_read<0>();
         }
     }
 
@@ -540,37 +655,38 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major tensor (rows x cols, leading dimension ld elements), box = box_cols x box_rows
+// 2-D row-major tensor (rows x cols, leading dimension ld elements; bf16 or fp32), box = box_cols x box_rows
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-             uint32_t box_rows) {
+             uint32_t box_rows, bool f32 = false) {
     EncodeTiledFn fn = get_encode_fn();
     SVAE_REQUIRE(fn != nullptr, SVAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    SVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0, SVAE_EALIGN,
-                 "bf16 matrices need 16-byte aligned base and leading dimension %% 8 == 0");
+    const uint64_t esz = f32 ? 4 : 2;
+    SVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld * esz) % 16) == 0, SVAE_EALIGN,
+                 "TMA operands need a 16-byte aligned base and row pitch");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * esz};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SVAE_REQUIRE(r == CUDA_SUCCESS, SVAE_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
     return SVAE_OK;
 }
 
-template <int MODE, int ACT, int DOTC, int CG>
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x, const TcParams& p,
            int grid, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG>;
+    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG, OUT32, RED>;
     if (!configured) {
-        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG)));
+        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG, MODE)));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes(CG);
+    cfg.blockDim = dim3(num_threads(CG));
+    cfg.dynamicSmemBytes = smem_bytes(CG, MODE);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -584,32 +700,34 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, con
     return SVAE_OK;
 }
 
-template <int MODE, int ACT, int DOTC>
-int launch_cg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
-              const TcParams& p, int cg, int grid, cudaStream_t st) {
-    if (cg == 2) return launch<MODE, ACT, DOTC, 2>(a, b, o, x, p, grid, st);
-    return launch<MODE, ACT, DOTC, 1>(a, b, o, x, p, grid, st);
-}
-
+// dispatch on the run-time options; only the combinations the library uses are instantiated
 template <int MODE, int ACT>
-int launch_dot(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
-               const TcParams& p, int cg, int grid, cudaStream_t st) {
-    if (MODE != 0 || p.o_accum == nullptr) return launch_cg<MODE, ACT, 0>(a, b, o, x, p, cg, grid, st);
-    switch (p.dot_c) {
-        case 1: return launch_cg<0, ACT, 1>(a, b, o, x, p, cg, grid, st);
-        case 2: return launch_cg<0, ACT, 2>(a, b, o, x, p, cg, grid, st);
-        default: return launch_cg<0, ACT, 3>(a, b, o, x, p, cg, grid, st);
+int launch_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
+                   const TcParams& p, int cg, int grid, cudaStream_t st) {
+#define SVAE_TC_LAUNCH(M_, D_, O_, R_)                                                         \
+    (cg == 2 ? launch<M_, ACT, D_, 2, O_, R_>(a, b, o, x, p, grid, st)                          \
+             : launch<M_, ACT, D_, 1, O_, R_>(a, b, o, x, p, grid, st))
+    if (MODE == 0) {
+        if (p.out_f32) return SVAE_TC_LAUNCH(0, 0, true, false);
+        if (p.o_accum == nullptr) return SVAE_TC_LAUNCH(0, 0, false, false);
+        if (p.dot_c == 1) return SVAE_TC_LAUNCH(0, 1, false, false);
+        if (p.dot_c == 2) return SVAE_TC_LAUNCH(0, 2, false, false);
+        return SVAE_TC_LAUNCH(0, 3, false, false);
     }
+    if (p.out_f32) return SVAE_TC_LAUNCH(1, 0, true, false);
+    if (p.red_S != nullptr) return SVAE_TC_LAUNCH(1, 0, false, true);
+    return SVAE_TC_LAUNCH(1, 0, false, false);
+#undef SVAE_TC_LAUNCH
 }
 
 template <int MODE>
 int launch_act(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
                const TcParams& p, int cg, int grid, cudaStream_t st) {
     switch (p.act) {
-        case SVAE_ACT_TANH: return launch_dot<MODE, SVAE_ACT_TANH>(a, b, o, x, p, cg, grid, st);
-        case SVAE_ACT_LEAKYRELU: return launch_dot<MODE, SVAE_ACT_LEAKYRELU>(a, b, o, x, p, cg, grid, st);
-        case SVAE_ACT_RELU: return launch_dot<MODE, SVAE_ACT_RELU>(a, b, o, x, p, cg, grid, st);
-        case SVAE_ACT_SIGMOID: return launch_dot<MODE, SVAE_ACT_SIGMOID>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_TANH: return launch_variant<MODE, SVAE_ACT_TANH>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_LEAKYRELU: return launch_variant<MODE, SVAE_ACT_LEAKYRELU>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_RELU: return launch_variant<MODE, SVAE_ACT_RELU>(a, b, o, x, p, cg, grid, st);
+        case SVAE_ACT_SIGMOID: return launch_variant<MODE, SVAE_ACT_SIGMOID>(a, b, o, x, p, cg, grid, st);
         default: set_error("tc_gemm: unknown activation %d", p.act); return SVAE_EINVAL;
     }
 }
@@ -638,40 +756,47 @@ int sm_count() {
 }  // namespace
 
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
-            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
-            const float* out_w, int out_w_ld, int dot_c, float* o_accum) {
+            int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st, const TcExtra& ex) {
     SVAE_REQUIRE(mode >= 0 && mode <= 2, SVAE_EINVAL, "tc_gemm: unknown mode %d", mode);
     if (M <= 0 || N <= 0 || K <= 0) return SVAE_OK;
     TcParams p{};
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_n = bias_n; p.aux = reinterpret_cast<const __nv_bfloat16*>(aux); p.ldaux = ldaux;
     p.act = act; p.out = out; p.ldo = ldo;
+    p.out_w = ex.out_w; p.out_w_ld = ex.out_w_ld; p.dot_c = ex.dot_c; p.o_accum = ex.o_accum;
+    p.out_f32 = (ex.out_f32 && mode != 2) ? 1 : 0;
+    p.red_S = (mode == 1) ? ex.red_S : nullptr; p.red_ld = ex.red_ld; p.red_grid = ex.red_grid;
+    p.red_P = ex.red_P; p.red_b0 = ex.red_b0;
+    const bool f32 = p.out_f32 != 0;
+    const bool red = p.red_S != nullptr;
+    const uint32_t ebox = f32 ? 32 : 64;          // epilogue block: 128 bytes of columns
     const int cg = cta_group_size();
     p.m_tiles = ceil_div(M, BM * cg);
     p.n_tiles = ceil_div(N, BN);
     p.k_blocks = ceil_div(K, BK);
     p.k_splits = 1;
     p.k_blocks_per_split = p.k_blocks;
-    p.out_w = out_w; p.out_w_ld = out_w_ld; p.dot_c = dot_c; p.o_accum = o_accum;
     CUtensorMap ma, mb, mo, mx;
     memset(&mo, 0, sizeof(mo));
     memset(&mx, 0, sizeof(mx));
     const int sms = sm_count();
     if (mode == 0) {
-        SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0 && N <= MAX_BIAS, SVAE_EINVAL, "tc_gemm fwd: N, K must be multiples of 64 and N <= %d", MAX_BIAS);
-        SVAE_REQUIRE(ldo % 8 == 0, SVAE_EALIGN, "tc_gemm: output leading dimension %% 8 != 0");
-        SVAE_REQUIRE(o_accum == nullptr || (mode == 0 && dot_c >= 1 && dot_c <= MAX_DOT_C && out_w != nullptr),
-                     SVAE_EINVAL, "tc_gemm fwd: fused output dot supports 1..%d channels", MAX_DOT_C);
+        SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm fwd: N, K must be multiples of 64");
+        SVAE_REQUIRE(!(f32 && ex.o_accum != nullptr), SVAE_EINVAL, "tc_gemm fwd: fp32 output cannot fuse the output dot");
+        SVAE_REQUIRE(ex.o_accum == nullptr || (ex.dot_c >= 1 && ex.dot_c <= MAX_DOT_C && ex.out_w != nullptr), SVAE_EINVAL,
+                     "tc_gemm fwd: fused output dot supports 1..%d channels", MAX_DOT_C);
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, N, K, ldw, 64, 256 / cg));
-        SVAE_TRY(make_map(&mo, out, M, N, ldo, 64, 128));
+        SVAE_TRY(make_map(&mo, out, M, N, ldo, ebox, 128, f32));
     } else if (mode == 1) {
         SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm dx: N, K must be multiples of 64");
-        SVAE_REQUIRE(ldo % 8 == 0 && ldaux % 8 == 0 && aux != nullptr, SVAE_EALIGN, "tc_gemm dx: aux/out alignment");
+        SVAE_REQUIRE(aux != nullptr, SVAE_EINVAL, "tc_gemm dx: aux is required");
+        SVAE_REQUIRE(!(red && f32), SVAE_EINVAL, "tc_gemm dx: the fused reduction works on the bf16 path");
+        SVAE_REQUIRE(!red || (ex.red_grid != nullptr && ex.red_P > 0), SVAE_EINVAL, "tc_gemm dx: reduction needs the grid");
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, K, N, ldw, 64, 64));
-        SVAE_TRY(make_map(&mo, out, M, N, ldo, 64, 128));
-        SVAE_TRY(make_map(&mx, aux, M, N, ldaux, 64, 128));
+        if (!red) SVAE_TRY(make_map(&mo, out, M, N, ldo, ebox, 128, f32));
+        SVAE_TRY(make_map(&mx, aux, M, N, ldaux, ebox, 128, f32));
     } else {
         // A: (K rows) x (lda cols) with M <= lda logical columns; Bm: (K rows) x (ldw cols), N <= ldw
         SVAE_TRY(make_map(&ma, A, K, round_up(M, 64) <= lda ? round_up(M, 64) : lda, lda, 64, 64));
@@ -689,7 +814,8 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     const int grid = (tiles < groups ? tiles : groups) * cg;
     if (mode == 0) return launch_act<0>(ma, mb, mo, mx, p, cg, grid, st);
     if (mode == 1) return launch_act<1>(ma, mb, mo, mx, p, cg, grid, st);
-    return launch_cg<2, SVAE_ACT_TANH, 0>(ma, mb, mo, mx, p, cg, grid, st);
+    if (cg == 2) return launch<2, SVAE_ACT_TANH, 0, 2, false, false>(ma, mb, mo, mx, p, grid, st);
+    return launch<2, SVAE_ACT_TANH, 0, 1, false, false>(ma, mb, mo, mx, p, grid, st);
 }
 
 }  // namespace svae
