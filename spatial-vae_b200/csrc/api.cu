@@ -1,6 +1,7 @@
 // C-ABI entry points of libsvae_b200.so and the host-side orchestration of one step.
 // See include/svae_b200.h for the contract and the reference call sites each entry replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -195,7 +196,7 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
     w.B = a_top; w.sBk = Hqp; w.sBn = 1;
     w.C = gq.w[s.Lq]; w.ldc = s.Hq;
     w.M = 2 * s.I; w.N = s.Hq; w.K = s.B;
-    w.accumulate = 1; w.split_k = s.B >= 2048 ? 8 : (s.B >= 512 ? 4 : 1);
+    w.accumulate = 1; w.split_k = s.B >= 512 ? 8 : (s.B >= 128 ? 2 : 1);
     SVAE_TRY(sgemm(w, e.st));
     SVAE_TRY(col_sum<float>(g_out, s.B, 2 * s.I, 2 * s.I, gq.b[s.Lq], e.st));
     SgemmArgs d{};
@@ -378,10 +379,12 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     int cur = 0;
     SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.f(d.p->g_o), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
                              g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
-    // FAST, grid coordinates, P fits the int16 image table: the last dX GEMM reduces delta_0 per image in its
-    // epilogue (S must be zero on entry) instead of storing it and re-reading it in image_col_reduce.
-    const bool fuse_red = !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr && g_x == nullptr &&
-                          (long)s.B < 32000;
+    // Optional (SVAE_FUSE_RED=1): the last dX GEMM reduces delta_0 per image in its epilogue (S zero on entry)
+    // instead of storing it for image_col_reduce.  Measured in round 1: 704 us vs 482 + 174 us at C2 -- the
+    // SIMT reduction in the epilogue costs more than the HBM pass it removes -- so it is off by default.
+    static const bool want_red = (getenv("SVAE_FUSE_RED") != nullptr && getenv("SVAE_FUSE_RED")[0] == '1');
+    const bool fuse_red = want_red && !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr &&
+                          g_x == nullptr && (long)s.B < 32000;
     bool reduced = false;
     for (int l = s.L - 1; l >= 1; --l) {
         RedSpec red;
@@ -436,6 +439,7 @@ static int first_layer_param_grads(const SvaeShape& s, const SvaeConfig& c, cons
         w.C = g.latent_w; w.ldc = s.Z;
         w.M = s.H; w.N = s.Z; w.K = s.B;
         w.accumulate = 1;
+        w.split_k = s.B >= 512 ? 8 : (s.B >= 128 ? 2 : 1);     // few output tiles: spread the long K over more CTAs
         SVAE_TRY(sgemm(w, st));
         if (dz) {
             // dz (B,Z) = z_scale * S_s Wz

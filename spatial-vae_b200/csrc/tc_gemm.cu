@@ -4,8 +4,7 @@
 // epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue while the next tile's
 // MMAs run.  Persistent CTAs, one per SM.  CG = 2 pairs two SMs (cta_group::2, cluster of 2): the pair
 // computes a 256 x 256 tile, each CTA stages its own 128 A rows and HALF of the B tile, so the weight /
-// operand traffic through L2 and shared memory per FLOP halves; the pair kernel also runs TWO epilogue
-// warp-groups (one warp per scheduler was latency bound: ncu showed 23 % issue utilisation).
+// operand traffic through L2 and shared memory per FLOP halves.
 //
 //   mode 0  FWD : out[M,N]  = act(A[M,K] W[N,K]^T + bias)              A K-major,  B K-major
 //                 (+ optional fused output layer: o[m,c] += sum_n h[m,n] W_o[c,n])
@@ -27,12 +26,16 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 rows (or 1
 constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64x64 bf16 TMA box (MN-major operands)
 constexpr int MAX_DOT_C = 3;                  // output channels the fused output-layer dot supports
 constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 128-byte epilogue block (SWIZZLE_128B)
-__host__ __device__ constexpr int epi_groups(int cg) { return cg == 2 ? 2 : 1; }             // epilogue warp-groups
+// Epilogue warp-groups per CTA.  Two groups were measured (round 1): no gain for fwd (the pair kernel is bound
+// by L2->SM operand bandwidth, not by epilogue latency) and they cost dX one ring stage, so one group is used.
+__host__ __device__ constexpr int epi_groups(int cg) { return (void)cg, 1; }
 __host__ __device__ constexpr int num_threads(int cg) { return 128 + 128 * epi_groups(cg); }
 __host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }        // 32 KB | 16 KB
 __host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
 // ring depth: whatever the staging blocks leave (mode 1 needs aux blocks too)
-__host__ __device__ constexpr int stages_of(int cg, int mode) { return cg == 2 ? (mode == 1 ? 3 : 4) : 3; }
+__host__ __device__ constexpr int stages_of(int cg, int mode) {
+    return cg == 2 ? ((mode == 1 && epi_groups(cg) == 2) ? 3 : 4) : 3;
+}
 // shared-memory map after the operand ring:
 //   2 output staging blocks per epilogue group | (mode 1) 2 aux blocks per group |
 //   tables: mode 0: 2 x (bias[BN] + W_o[3][BN]) floats; mode 1 RED: 2 x (x[128], y[128], image[128]) | barriers
@@ -50,7 +53,9 @@ __host__ __device__ constexpr int table_bytes(int mode) {
 __host__ __device__ constexpr int off_bars(int cg, int mode) { return off_tables(cg, mode) + table_bytes(mode); }
 // The dynamic shared memory is declared 1024-byte aligned; the pair dX kernel has no room for alignment slack
 // (it traps if the base ever comes back misaligned), the others keep 1 KB of slack and align by hand.
-__host__ __device__ constexpr int align_slack(int cg, int mode) { return (cg == 2 && mode == 1) ? 0 : 1024; }
+__host__ __device__ constexpr int align_slack(int cg, int mode) {
+    return (cg == 2 && mode == 1 && epi_groups(cg) == 2) ? 0 : 1024;
+}
 __host__ __device__ constexpr int smem_bytes(int cg, int mode) { return off_bars(cg, mode) + 256 + align_slack(cg, mode); }
 static_assert(smem_bytes(1, 0) <= 232448 && smem_bytes(1, 1) <= 232448 && smem_bytes(2, 0) <= 232448 &&
               smem_bytes(2, 1) <= 232448 && smem_bytes(2, 2) <= 232448, "shared memory budget");
