@@ -292,6 +292,13 @@ def main():
     if sampler:
         sampler.stop()
     last = [float(v) for v in res.cpu()]
+    # CPU time to ENQUEUE one step (short burst on an idle queue, so the launch queue never fills)
+    torch.cuda.synchronize()
+    t_host0 = time.perf_counter()
+    for i in range(8):
+        device_step(i)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / 8
+    torch.cuda.synchronize()
 
     # ---- end to end through the public API with HOST buffers ---------------------------------------
     host_data = synth_images(c, 2 * B, torch.device("cpu"), 99 + rank).pin_memory()
@@ -347,6 +354,7 @@ def main():
         "step_tflops_algorithmic": value * fl_img / 1e12,
         "step_frac_of_sustained_bf16": value * fl_img / 1e12 / (sustained * world),
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_ms,
         "last_step": {"elbo": last[0], "logp": last[1], "kl": last[2]},
         "clocks": sampler.summary() if sampler else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},

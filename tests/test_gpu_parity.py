@@ -383,3 +383,61 @@ def test_adam_trajectory_matches_reference(precision):
         frac = float((diff < 1e-4).float().mean())
         print(f"fast precision: max |dparam| {float(diff.max()):.3e}, within 1e-4: {frac:.5f}")
         assert frac > 0.99 and float(diff.max()) < 2.5e-3   # 2.5e-3 > 10 steps * lr: sign flips only
+
+
+# ---- full BASELINE sizes: size-independent properties + fast-vs-parity agreement -------------------------
+def _full_case(cfgname):
+    import bench
+    c = dict(bench.CONFIGS[cfgname])
+    P = c["n"] * c["n"]
+    dec, enc = O.init_params(P * c["Cin"], c["Z"] + 3, c["Z"], c["H"], c["L"], c["Hq"], c["Lq"], c["C"], seed=1)
+    y = bench.synth_images(c, c["B"], torch.device("cpu"), 1234)
+    eps = torch.randn(c["B"], c["Z"] + 3, generator=torch.Generator().manual_seed(1000))
+    cfg = O.StepConfig(family=c["family"], theta_prior=c["theta_prior"])
+    return c, dec, enc, O.make_grid(c["n"], c["n"]), y, eps, cfg
+
+
+def test_c2_full_size_properties():
+    """configs[1] at its full size (28x28, z=100, 500x2, B=1024): the minibatch decomposes over images
+    (what data parallelism relies on), fast and parity precision agree within the north-star tolerance, and
+    the outputs respect their ranges."""
+    c, dec, enc, grid, y, eps, cfg = _full_case("c2")
+    B = c["B"]
+    sf, yh, gf = _run_cuda(cfg, dec, enc, grid, y, eps, "fast")
+    sp, _, gp = _run_cuda(cfg, dec, enc, grid, y, eps, "parity")
+    rel = (sf[:, 2] - sp[:, 2]).abs() / sp[:, 2].abs()
+    assert float(rel.max()) <= 1e-3, f"fast vs parity per-image ELBO: {float(rel.max()):.2e}"
+    assert float(sf[:, 1].min()) >= 0.0                      # KL terms are non-negative
+    assert float(yh.min()) > 0.0 and float(yh.max()) < 1.0   # sigmoid outputs
+    # two half batches with grad_scale = 1/B: same per-image values, gradients add up
+    h = B // 2
+    sa, _, ga = _run_cuda(cfg, dec, enc, grid, y[:h], eps[:h], "fast", grad_scale=1.0 / B)
+    sb, _, gb = _run_cuda(cfg, dec, enc, grid, y[h:], eps[h:], "fast", grad_scale=1.0 / B)
+    np.testing.assert_allclose(torch.cat([sa, sb]).numpy(), sf.numpy(), rtol=2e-6, atol=1e-4)
+    for i, (a, b, full) in enumerate(zip(ga, gb, gf)):
+        scale = float(full.abs().max()) + 1e-12
+        assert float((a + b - full).abs().max()) <= 2e-3 * scale, f"grad {i}"
+    # a permutation of the batch permutes the per-image results
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+    sq, _, _ = _run_cuda(cfg, dec, enc, grid, y[perm], eps[perm], "fast")
+    np.testing.assert_allclose(sq.numpy(), sf[perm].numpy(), rtol=2e-6, atol=1e-4)
+    # fast gradients track the fp32 ones
+    for i, (a, b) in enumerate(zip(gf, gp)):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 5e-2 * scale, f"fast vs parity grad {i}"
+
+
+@pytest.mark.parametrize("cfgname,B", [("c3", 12), ("c5", 8)])
+def test_particle_configs_at_full_model_size_against_oracle(cfgname, B):
+    """C3 (fit-noise) and C5 (39x39 CTF) model shapes, small batch: per-image ELBO vs the oracle."""
+    c, dec, enc, grid, y, eps, cfg = _full_case(cfgname)
+    y, eps = y[:B], eps[:B]
+    kw = {}
+    if c.get("ctf"):
+        kw["ctf"] = 0.03 * torch.randn(B, 1, c["ctf"], c["ctf"], generator=torch.Generator().manual_seed(5))
+    out, _ = O.step_grads(cfg, dec, enc, grid, y, eps, **kw)
+    ref = (out["logp_i"] - out["kl_i"]).numpy()
+    for precision, tol in (("parity", 2e-5), ("fast", 1e-3)):
+        stats, _, _ = _run_cuda(cfg, dec, enc, grid, y, eps, precision, **kw)
+        rel = np.abs(stats[:, 2].numpy() - ref) / np.abs(ref)
+        assert rel.max() <= tol, f"{cfgname} {precision}: {rel.max():.2e}"
