@@ -77,6 +77,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.25):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.stop_flag, self.max_mhz = index, period, [], False, None
+        self.query_ms = []
+        if os.environ.get("BENCH_NVML_PERIOD"):
+            self.period = float(os.environ["BENCH_NVML_PERIOD"])
 
     def run(self):
         try:
@@ -86,12 +89,17 @@ class ClockSampler(threading.Thread):
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            what = os.environ.get("BENCH_NVML", "both")
             while not self.stop_flag:
-                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                try:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                t0 = time.perf_counter()
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM) if what in ("both", "clock") else 0
+                mask = 0
+                if what in ("both", "reasons"):
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.query_ms.append((time.perf_counter() - t0) * 1e3)
                 self.samples.append((mhz, mask))
                 time.sleep(self.period)
         except Exception:
@@ -106,7 +114,48 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         mhz = sorted(s[0] for s in self.samples)
         reasons = [n for n, bit in self.REASONS.items() if any(s[1] & bit for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(mhz)}
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(mhz),
+                "nvml_query_ms": round(sum(self.query_ms) / len(self.query_ms), 2)}
+
+
+def nvml_reasons(index):
+    """(max SM MHz, set of active throttle reasons) read once through NVML, outside the timed region."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[index]) if vis and vis.split(",")[0].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        try:
+            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        return pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), {n for n, b in ClockSampler.REASONS.items() if mask & b}
+    except Exception:
+        return None, {"unavailable"}
+
+
+def clocks_summary(sampler, probe_mhz, before, after):
+    """sm_mhz = median of the on-device clock probes taken inside the timed region; reasons = union of the NVML
+    samples taken during the region (single GPU) and right before / after it (always)."""
+    out = {"sm_mhz": round(probe_mhz[len(probe_mhz) // 2]) if probe_mhz else None,
+           "sm_mhz_min": round(probe_mhz[0]) if probe_mhz else None,
+           "sm_max_mhz": (before or (None,))[0], "probes": len(probe_mhz),
+           "method": "on-device clock64/globaltimer probes during the timed region"}
+    reasons = set()
+    for r in (before, after):
+        if r:
+            reasons |= r[1]
+    if sampler is not None:
+        s = sampler.summary()
+        reasons |= set(s.get("reasons", []))
+        out["nvml_sm_mhz"] = s.get("sm_mhz")
+        out["nvml_samples"] = s.get("samples")
+        out["method"] += " + NVML at 4 Hz during it"
+    else:
+        out["method"] += " + NVML right before/after it (NVML polling during NCCL steps perturbs them)"
+    out["reasons"] = sorted(reasons)
+    return out
 
 
 def peaks():
@@ -268,7 +317,12 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
+    # NVML polling from a side thread measurably slows NCCL steps (+13 % at 2 GPUs even at 1 Hz), so with more
+    # than one rank the clock under load comes from on-device probes and NVML is read right before / after.
+    sampler = ClockSampler(local) if (rank == 0 and world == 1 and not os.environ.get("BENCH_NO_SAMPLER")) else None
+    probe_every = max(1, args.steps // 8)
+    probes = torch.zeros(args.steps // probe_every + 2, dtype=torch.float32, device=device)
+    reasons_before = nvml_reasons(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.1)           # first NVML sample lands before the timed region starts
@@ -276,10 +330,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    n_probe = 0
     for i in range(args.steps):
         res = device_step(i)
-        if os.environ.get("BENCH_SYNC_EACH"):
-            torch.cuda.synchronize()
+        if i % probe_every == probe_every // 2:      # ~8 probes of 20 us spread over the timed region
+            L.check(L.lib.svae_sm_clock_probe(probes[n_probe:].data_ptr(), torch.cuda.current_stream().cuda_stream),
+                    "svae_sm_clock_probe")
+            n_probe += 1
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -291,6 +348,8 @@ def main():
     total_ms = float(ms)
     if sampler:
         sampler.stop()
+    reasons_after = nvml_reasons(local) if rank == 0 else None
+    probe_mhz = sorted(float(v) for v in probes[:n_probe].cpu())
     last = [float(v) for v in res.cpu()]
     # CPU time to ENQUEUE one step (short burst on an idle queue, so the launch queue never fills)
     torch.cuda.synchronize()
@@ -356,7 +415,7 @@ def main():
         "gpu_launches": int(launches),
         "host_enqueue_ms_per_step": host_ms,
         "last_step": {"elbo": last[0], "logp": last[1], "kl": last[2]},
-        "clocks": sampler.summary() if sampler else None,
+        "clocks": clocks_summary(sampler, probe_mhz, reasons_before, reasons_after),
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
     }
     if args.precision == "fast" and c["L"] >= 2:

@@ -169,6 +169,10 @@ int  svae_adam_step(float* param, float* grad, float* m, float* v, size_t n,
 int  svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
                       void* stream);
 
+/* Measures the SM clock on the device: enqueues a one-thread kernel that spins ~20 us and writes
+ * cycles/time in MHz to *out_mhz (device pointer).  Measurement aid for bench.py. */
+int  svae_sm_clock_probe(float* out_mhz, void* stream);
+
 /* bf16 tensor-core GEMM building blocks (tcgen05 / TMEM / TMA), fp32 accumulation.
  *   mode 0  FWD : out[M,N]  = act(A[M,K] * W[N,K]^T + bias[N])                   (bf16 out)
  *   mode 1  DX  : out[M,N]  = (A[M,K] * W[K,N]) .* act'(aux[M,N])                (bf16 out)

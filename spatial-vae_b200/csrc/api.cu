@@ -672,6 +672,11 @@ int svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t
     return gather_rows(src, index, dst, n_rows, row_len, (cudaStream_t)stream);
 }
 
+int svae_sm_clock_probe(float* out_mhz, void* stream) {
+    SVAE_REQUIRE(out_mhz != nullptr, SVAE_EINVAL, "null argument");
+    return clock_probe(out_mhz, (cudaStream_t)stream);
+}
+
 int svae_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* aux, int ldaux, int activation, void* out, int ldo, void* stream) {
     SVAE_REQUIRE(A && W && out, SVAE_EINVAL, "null argument");

@@ -71,6 +71,9 @@ int gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows
 // dst (rows_p x cols_p, bf16, zero padded) = src (rows x cols fp32)
 int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p, cudaStream_t st);
 
+// SM clock in MHz measured on the device (20 us spin of one thread)
+int clock_probe(float* out_mhz, cudaStream_t st);
+
 // fp32 -> (hi, hi|lo, lo|hi) bf16 terms for the 3-MMA error-compensated encoder GEMMs (see step_kernels.cu)
 int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, int rows_p, int cols_p, int kcat,
            int pattern, cudaStream_t st);

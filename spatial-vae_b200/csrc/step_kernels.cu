@@ -850,6 +850,24 @@ int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// SM clock probe: one thread spins ~20 us and reports cycles / wall time.  bench.py enqueues it between steps
+// to sample the clock under load without NVML (whose queries were measured to stall NCCL steps).
+// ------------------------------------------------------------------------------------------------
+__global__ void clock_probe_k(float* out_mhz) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 20000ull);
+    const long long c1 = clock64();
+    *out_mhz = (float)((double)(c1 - c0) * 1e3 / (double)(t1 - t0));
+}
+int clock_probe(float* out_mhz, cudaStream_t st) {
+    clock_probe_k<<<1, 1, 0, st>>>(out_mhz);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 -> three bf16 terms for error-compensated tensor-core GEMMs (encoder):
 //   x = hi + lo (+ 2^-17 |x|),  A*B ~ Ahi*Bhi + Ahi*Blo + Alo*Bhi
 // pattern 0 ("A side") emits (hi, hi, lo), pattern 1 ("B side") emits (hi, lo, hi); the three terms are laid
