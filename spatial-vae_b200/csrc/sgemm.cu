@@ -7,10 +7,10 @@
 namespace svae {
 
 template <int BM, int BN, int BK, int TM, int TN, bool A_KCONTIG, bool B_KCONTIG>
-__global__ void __launch_bounds__(256) sgemm_kernel(SgemmArgs g, int k_chunk) {
-    constexpr int NT = 256;
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(SgemmArgs g, int k_chunk) {
+    constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int PAD = 4;
-    static_assert((BM / TM) * (BN / TN) == NT, "thread tile mismatch");
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/thread mismatch");
     static_assert(TM % 4 == 0 && TN % 4 == 0, "micro tile must be float4 multiples");
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
@@ -124,10 +124,11 @@ static int launch_cfg(const SgemmArgs& a, cudaStream_t st) {
     const bool ak = (a.sAk == 1), bk = (a.sBk == 1);
     if (!ak && a.sAm != 1) { set_error("sgemm: A has no unit stride"); return SVAE_EINVAL; }
     if (!bk && a.sBn != 1) { set_error("sgemm: B has no unit stride"); return SVAE_EINVAL; }
-    if (ak && bk)        sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, 256, 0, st>>>(a, k_chunk);
-    else if (ak && !bk)  sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, 256, 0, st>>>(a, k_chunk);
-    else if (!ak && bk)  sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, 256, 0, st>>>(a, k_chunk);
-    else                 sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, 256, 0, st>>>(a, k_chunk);
+    constexpr int NT = (BM / TM) * (BN / TN);
+    if (ak && bk)        sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, NT, 0, st>>>(a, k_chunk);
+    else if (ak && !bk)  sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, NT, 0, st>>>(a, k_chunk);
+    else if (!ak && bk)  sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, NT, 0, st>>>(a, k_chunk);
+    else                 sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, NT, 0, st>>>(a, k_chunk);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
@@ -142,7 +143,11 @@ int sgemm(const SgemmArgs& a_in, cudaStream_t st) {
     }
     const long big_tiles = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * (a.split_k > 1 ? a.split_k : 1);
     if (big_tiles >= 120) return launch_cfg<128, 128, 8, 8>(a, st);
-    return launch_cfg<64, 64, 4, 4>(a, st);
+    // few 64x64 tiles: these GEMMs are latency bound (one CTA per SM walking K), so cut the tile to get more,
+    // shorter CTAs in flight
+    const long mid_tiles = (long)ceil_div(a.M, 64) * ceil_div(a.N, 64) * (a.split_k > 1 ? a.split_k : 1);
+    if (mid_tiles >= 296) return launch_cfg<64, 64, 4, 4>(a, st);
+    return launch_cfg<32, 32, 4, 4>(a, st);
 }
 
 }  // namespace svae
