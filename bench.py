@@ -32,7 +32,8 @@ CONFIGS = {
     # name: family, n (image side), Cin, C_out, Z, H, L, Hq, Lq, batch per GPU, theta_prior, ctf
     "c1": dict(family="mnist", n=28, Cin=1, C=1, Z=2, H=500, L=2, Hq=500, Lq=2, B=100, theta_prior=math.pi / 4),
     "c2": dict(family="mnist", n=28, Cin=1, C=1, Z=100, H=500, L=2, Hq=500, Lq=2, B=1024, theta_prior=math.pi / 4),
-    "c3": dict(family="particles", n=40, Cin=1, C=2, Z=2, H=500, L=2, Hq=500, Lq=2, B=512, theta_prior=math.pi),
+    "c3": dict(family="particles", n=40, Cin=1, C=2, Z=2, H=500, L=2, Hq=500, Lq=2, B=512, theta_prior=math.pi,
+               augment=True),
     "c4": dict(family="galaxy", n=64, Cin=3, C=3, Z=20, H=1000, L=4, Hq=5000, Lq=2, B=128, theta_prior=math.pi),
     "c5": dict(family="particles", n=40, Cin=1, C=1, Z=2, H=500, L=2, Hq=500, Lq=2, B=4096, theta_prior=math.pi,
                ctf=39),
@@ -40,7 +41,7 @@ CONFIGS = {
 WORKLOAD_TEXT = {
     "c1": "train_mnist.py rotated MNIST 28x28, z-dim 2, p-hidden 500x2, minibatch 100",
     "c2": "rotated+translated MNIST 28x28, z-dim 100, p-hidden 500x2, minibatch 1024 per GPU",
-    "c3": "5HDB-like EM particles 40x40, --fit-noise, minibatch 512 per GPU (no augmentation)",
+    "c3": "5HDB-like EM particles 40x40, --fit-noise, --augment-rotation (device bicubic), minibatch 512 per GPU",
     "c4": "galaxy zoo 64x64x3, z-dim 20, p-hidden 1000x4, q-hidden 5000x2, minibatch 128 per GPU",
     "c5": "CODH/ACS-like EM particles 40x40 with 39x39 CTF kernels, minibatch 4096 per GPU",
 }
@@ -305,12 +306,19 @@ def main():
         ctf_all = 0.03 * torch.randn(n_data, c["ctf"], c["ctf"], device=device,
                                      generator=torch.Generator(device=device).manual_seed(77 + rank))
     perm_gen = torch.Generator(device=device).manual_seed(4321)
+    import numpy as np
+    aug_rng = np.random.default_rng(7 + rank)
 
     def device_step(i):
         idx = torch.randperm(n_data, generator=perm_gen, device=device)[:B]
         y = SF.gather_rows(data, idx)
         ctf = SF.gather_rows(ctf_all, idx) if ctf_all is not None else None
-        return trainer.step(grid, y, global_batch=B * world, ctf=ctf)
+        y_enc = theta_offset = None
+        if c.get("augment"):      # --augment-rotation: encoder sees a randomly rotated copy, decoder theta gets the offset
+            offs = aug_rng.uniform(0, 2 * math.pi, size=B)
+            y_enc = SF.rotate_bicubic(y, c["n"], c["n"], offs * (360 / 2 / math.pi))
+            theta_offset = torch.from_numpy(offs).float().to(device, non_blocking=True)
+        return trainer.step(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
 
     for i in range(args.warmup):
         device_step(i)
@@ -370,7 +378,12 @@ def main():
         lo = (i % 2) * B
         y = host_data[lo:lo + B].to(device, non_blocking=True)
         ctf = host_ctf[lo:lo + B].to(device, non_blocking=True) if host_ctf is not None else None
-        r = trainer.step(grid, y, global_batch=B * world, ctf=ctf)
+        y_enc = theta_offset = None
+        if c.get("augment"):
+            offs = aug_rng.uniform(0, 2 * math.pi, size=B)
+            y_enc = SF.rotate_bicubic(y, c["n"], c["n"], offs * (360 / 2 / math.pi))
+            theta_offset = torch.from_numpy(offs).float().to(device, non_blocking=True)
+        r = trainer.step(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
         out_host.copy_(r, non_blocking=False)      # device -> host read of the step's result (syncs)
         return out_host
 

@@ -12,6 +12,7 @@
  *                                                                           train_galaxy.py:27-128,207-208
  *   svae_adam_step                     optim.step(); optim.zero_grad()      train_mnist.py:149-150 (Adam :389-392)
  *   svae_gather_rows                   DataLoader(TensorDataset, shuffle)   train_mnist.py:334,395-396
+ *   svae_rotate_bicubic                PIL Image.rotate(BICUBIC) loop       train_particles.py:28-43, train_galaxy.py:36-54
  *   svae_gemm_bf16                     one nn.Linear of SpatialGenerator.layers (models.py:82,126) on
  *                                      tcgen05 tensor cores (building block, exposed for tests)
  *
@@ -168,6 +169,15 @@ int  svae_adam_step(float* param, float* grad, float* m, float* v, size_t n,
 /* dst[i, :] = src[index[i], :] for i < n_rows: one launch replaces the per-sample DataLoader fetch. */
 int  svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
                       void* stream);
+
+/* --augment-rotation on the device (reference train_particles.py:28-43, train_galaxy.py:36-54, which loop over
+ * the minibatch on the host with PIL): rotates B images (n_rows, n_cols, channels), fp32, about their centres,
+ * bit-compatible with Pillow's Image.rotate(angle, resample=BICUBIC).  inv_affine: (B, 6) float64 destination->
+ * source matrices as PIL/Image.py builds them; mode: (B) 0 = general, 1 = copy (angle 0), 2 = 180, 3 = 90, 4 = 270
+ * degrees (Pillow's transpose fast paths).  quantize_u8 != 0 reproduces the galaxy driver's round trip through
+ * uint8: sample = (uint8)(x*255), result = clip/truncate to uint8, then / 255. */
+int  svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, const int32_t* mode, int B,
+                         int n_rows, int n_cols, int channels, int quantize_u8, void* stream);
 
 /* Measures the SM clock on the device: enqueues a one-thread kernel that spins ~20 us and writes
  * cycles/time in MHz to *out_mhz (device pointer).  Measurement aid for bench.py. */

@@ -672,6 +672,13 @@ int svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t
     return gather_rows(src, index, dst, n_rows, row_len, (cudaStream_t)stream);
 }
 
+int svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, const int32_t* mode, int B, int n_rows,
+                        int n_cols, int channels, int quantize_u8, void* stream) {
+    SVAE_REQUIRE(src && dst && inv_affine && mode, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(B >= 0 && n_rows > 0 && n_cols > 0 && channels >= 1 && channels <= 4, SVAE_EINVAL, "bad image shape");
+    return rotate_bicubic(src, dst, inv_affine, mode, B, n_rows, n_cols, channels, quantize_u8, (cudaStream_t)stream);
+}
+
 int svae_sm_clock_probe(float* out_mhz, void* stream) {
     SVAE_REQUIRE(out_mhz != nullptr, SVAE_EINVAL, "null argument");
     return clock_probe(out_mhz, (cudaStream_t)stream);

@@ -71,6 +71,10 @@ int gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows
 // dst (rows_p x cols_p, bf16, zero padded) = src (rows x cols fp32)
 int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p, cudaStream_t st);
 
+// Pillow-compatible bicubic rotation of B images (h, w, C) about their centres (see step_kernels.cu)
+int rotate_bicubic(const float* src, float* dst, const double* mat, const int* mode, int B, int h, int w, int C,
+                   int quantize_u8, cudaStream_t st);
+
 // SM clock in MHz measured on the device (20 us spin of one thread)
 int clock_probe(float* out_mhz, cudaStream_t st);
 

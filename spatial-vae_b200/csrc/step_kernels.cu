@@ -850,6 +850,106 @@ int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bicubic rotation of a minibatch about the image centre, bit-compatible with Pillow's
+// Image.rotate(angle, resample=BICUBIC) as the reference uses it for --augment-rotation
+// (train_particles.py:39-43 on float32 images, train_galaxy.py:47-54 through uint8).  Pillow resamples in
+// double precision with the a = -1 cubic: 4x4 window with clamped columns, rows outside the image repeat the
+// previous row's value, destination pixels that map outside the source are 0; for float images the
+// coefficient sums of the horizontal pass are float32 (C float arithmetic), integer samples are exact.
+// Explicit _rn intrinsics keep nvcc from contracting a*b+c into FMAs, which would change the rounding.
+// mode: 0 general (inverse affine in mat[b*6..]), 1 copy, 2 rot180, 3 rot90 (ccw), 4 rot270.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double horner3(double p1, double p2, double p3, double p4, double d) {
+    return __dadd_rn(p1, __dmul_rn(d, __dadd_rn(p2, __dmul_rn(d, __dadd_rn(p3, __dmul_rn(d, p4))))));
+}
+__device__ __forceinline__ double cubic_f32(float v1, float v2, float v3, float v4, double d) {
+    const float p2 = __fadd_rn(-v1, v3);
+    const float p3 = __fsub_rn(__fadd_rn(__fmul_rn(2.f, __fsub_rn(v1, v2)), v3), v4);
+    const float p4 = __fadd_rn(__fsub_rn(__fadd_rn(-v1, v2), v3), v4);
+    return horner3((double)v2, (double)p2, (double)p3, (double)p4, d);
+}
+__device__ __forceinline__ double cubic_f64(double v1, double v2, double v3, double v4, double d) {
+    const double p2 = __dadd_rn(-v1, v3);
+    const double p3 = __dsub_rn(__dadd_rn(__dmul_rn(2.0, __dsub_rn(v1, v2)), v3), v4);
+    const double p4 = __dadd_rn(__dsub_rn(__dadd_rn(-v1, v2), v3), v4);
+    return horner3(v2, p2, p3, p4, d);
+}
+
+template <bool U8>
+__global__ void rotate_bicubic_k(const float* __restrict__ src, float* __restrict__ dst, const double* __restrict__ mat,
+                                 const int* __restrict__ mode, int B, int h, int w, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)B * h * w) return;
+    const int b = (int)(idx / (h * w));
+    const int pix = (int)(idx % (h * w));
+    const int i = pix / w, j = pix % w;
+    const float* im = src + (long)b * h * w * C;
+    float* o = dst + ((long)b * h * w + pix) * C;
+    const int md = mode[b];
+    auto sample = [&](int r, int c, int ch) -> float {      // the value Pillow sees at (row r, col c)
+        const float v = im[((long)r * w + c) * C + ch];
+        return U8 ? (float)(unsigned char)__fmul_rn(v, 255.f) : v;
+    };
+    auto emit = [&](int ch, double v, bool inside) {
+        if (U8) {
+            const double q = !inside ? 0.0 : (v <= 0.0 ? 0.0 : (v >= 255.0 ? 255.0 : floor(v)));
+            o[ch] = (float)__ddiv_rn(q, 255.0);
+        } else {
+            o[ch] = inside ? (float)v : 0.f;
+        }
+    };
+    if (md != 0) {
+        int r = i, c = j;
+        if (md == 2) { r = h - 1 - i; c = w - 1 - j; }
+        else if (md == 3) { r = j; c = w - 1 - i; }
+        else if (md == 4) { r = h - 1 - j; c = i; }
+        for (int ch = 0; ch < C; ++ch) emit(ch, (double)sample(r, c, ch), true);
+        return;
+    }
+    const double* m = mat + (long)b * 6;
+    const double xs = j + 0.5, ys = i + 0.5;
+    double xin = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xs), __dmul_rn(m[1], ys)), m[2]);
+    double yin = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xs), __dmul_rn(m[4], ys)), m[5]);
+    const bool inside = (xin >= 0.0) && (xin < (double)w) && (yin >= 0.0) && (yin < (double)h);
+    if (!inside) {
+        for (int ch = 0; ch < C; ++ch) emit(ch, 0.0, false);
+        return;
+    }
+    xin -= 0.5; yin -= 0.5;
+    int x = (int)floor(xin), y = (int)floor(yin);
+    const double dx = xin - x, dy = yin - y;
+    --x; --y;
+    int cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cc[k] = min(max(x + k, 0), w - 1);
+    for (int ch = 0; ch < C; ++ch) {
+        double rowv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = y + k;
+            if (k == 0 || (yy >= 0 && yy < h)) {
+                const int r = min(max(yy, 0), h - 1);
+                const float a0 = sample(r, cc[0], ch), a1 = sample(r, cc[1], ch), a2 = sample(r, cc[2], ch),
+                            a3 = sample(r, cc[3], ch);
+                rowv[k] = U8 ? cubic_f64(a0, a1, a2, a3, dx) : cubic_f32(a0, a1, a2, a3, dx);
+            } else {
+                rowv[k] = rowv[k - 1];
+            }
+        }
+        emit(ch, cubic_f64(rowv[0], rowv[1], rowv[2], rowv[3], dy), true);
+    }
+}
+int rotate_bicubic(const float* src, float* dst, const double* mat, const int* mode, int B, int h, int w, int C,
+                   int quantize_u8, cudaStream_t st) {
+    const long n = (long)B * h * w;
+    if (n == 0) return SVAE_OK;
+    if (quantize_u8) rotate_bicubic_k<true><<<ceil_div(n, 256), 256, 0, st>>>(src, dst, mat, mode, B, h, w, C);
+    else rotate_bicubic_k<false><<<ceil_div(n, 256), 256, 0, st>>>(src, dst, mat, mode, B, h, w, C);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // SM clock probe: one thread spins ~20 us and reports cycles / wall time.  bench.py enqueues it between steps
 // to sample the clock under load without NVML (whose queries were measured to stall NCCL steps).
 // ------------------------------------------------------------------------------------------------

@@ -49,22 +49,11 @@ def eval_minibatch_mnist(x, y, p_net, q_net, rotate=True, translate=True, dx_sca
 
 
 def rotate_images_bicubic(y, n, offsets, channels=None):
-    """The reference's host-side augmentation (train_particles.py:36-43 / train_galaxy.py:44-54): PIL
-    bicubic rotation per image.  Host code on purpose: the device kernel is a listed next step
-    (SURVEY.md section 8f rank 1), the arithmetic lives in Pillow."""
-    from PIL import Image
-    out = y.clone()
-    for i in range(y.size(0)):
-        deg = 360 * offsets[i] / 2 / np.pi
-        if channels is None:
-            im = Image.fromarray(y[i].view(n, n).cpu().numpy())
-            im = im.rotate(deg, resample=Image.BICUBIC)
-            out[i] = torch.from_numpy(np.array(im)).to(y.device).view(-1)
-        else:
-            im = Image.fromarray((y[i].view(n, n, channels).cpu().numpy() * 255).astype(np.uint8))
-            im = im.rotate(deg, resample=Image.BICUBIC)
-            out[i] = torch.from_numpy(np.array(im).astype(float) / 255).to(y.device).view(-1, channels)
-    return out
+    """The reference's augmentation (train_particles.py:36-43 / train_galaxy.py:44-54) rotates every image of the
+    minibatch with PIL on the host (device -> host -> device round trip plus a Python loop).  Here the same
+    arithmetic (Pillow's bicubic affine resampling, uint8 round trip for RGB) runs in one kernel on the device."""
+    deg = 360 * np.asarray(offsets, dtype=np.float64) / 2 / np.pi
+    return SF.rotate_bicubic(y, n, n, deg, channels=channels or 1, quantize_u8=channels is not None)
 
 
 def _augment(y, rotate, augment_rotation, channels=None):

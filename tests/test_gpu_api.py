@@ -209,3 +209,28 @@ def test_command_lines_train_on_synthetic_data(script, argv, cols, capsys):
     vals = [float(r[-3]) for r in rows]         # ELBO column
     assert all(math.isfinite(v) for v in vals)
     assert vals[2] > vals[0]                    # the training ELBO improves from epoch 1 to epoch 2
+
+
+def test_device_bicubic_rotation_is_bit_exact_with_the_pillow_port():
+    """svae_rotate_bicubic against oracle/pillow_rotate.py (itself bit exact with Pillow, see the CPU tests):
+    float32 particles and the uint8 round trip of the galaxy driver."""
+    dev = _dev()
+    import spatial_vae.functional as SF
+    from oracle.pillow_rotate import rotate_bicubic
+    rng = np.random.default_rng(3)
+    for n, B in ((40, 9), (7, 5), (28, 6)):
+        y = rng.standard_normal((B, n * n)).astype(np.float32)
+        deg = rng.uniform(0, 360, B)
+        deg[:4] = [0.0, 90.0, 180.0, 270.0]
+        got = SF.rotate_bicubic(torch.from_numpy(y).to(dev), n, n, deg).cpu().numpy()
+        for b in range(B):
+            ref = rotate_bicubic(y[b].reshape(n, n), float(deg[b])).reshape(-1)
+            assert np.array_equal(got[b], ref), (n, b, deg[b], np.abs(got[b] - ref).max())
+    n, B = 16, 6
+    y = rng.random((B, n * n, 3)).astype(np.float32)
+    deg = rng.uniform(0, 360, B)
+    got = SF.rotate_bicubic(torch.from_numpy(y).to(dev), n, n, deg, channels=3, quantize_u8=True).cpu().numpy()
+    for b in range(B):
+        u8 = (y[b].reshape(n, n, 3) * 255).astype(np.uint8)
+        ref = (rotate_bicubic(u8, float(deg[b])).astype(float) / 255).astype(np.float32).reshape(-1, 3)
+        assert np.array_equal(got[b], ref), (b, np.abs(got[b] - ref).max())
