@@ -176,6 +176,11 @@ int  svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_
  * source matrices as PIL/Image.py builds them; mode: (B) 0 = general, 1 = copy (angle 0), 2 = 180, 3 = 90, 4 = 270
  * degrees (Pillow's transpose fast paths).  quantize_u8 != 0 reproduces the galaxy driver's round trip through
  * uint8: sample = (uint8)(x*255), result = clip/truncate to uint8, then / 255. */
+/* HOST helper (host pointers, no device work): the (B, 6) destination->source matrices and (B) modes that
+ * svae_rotate_bicubic takes, for counter-clockwise angles in degrees, built exactly as PIL/Image.py rotate() does
+ * (angle % 360, math.radians, cos/sin rounded to 15 decimals, rotation about (w/2, h/2)). */
+int  svae_rotation_matrices(const double* angles_deg, int B, int n_rows, int n_cols, double* inv_affine,
+                            int32_t* mode);
 int  svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, const int32_t* mode, int B,
                          int n_rows, int n_cols, int channels, int quantize_u8, void* stream);
 

@@ -1,5 +1,6 @@
 // C-ABI entry points of libsvae_b200.so and the host-side orchestration of one step.
 // See include/svae_b200.h for the contract and the reference call sites each entry replaces.
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -677,6 +678,33 @@ int svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, 
     SVAE_REQUIRE(src && dst && inv_affine && mode, SVAE_EINVAL, "null argument");
     SVAE_REQUIRE(B >= 0 && n_rows > 0 && n_cols > 0 && channels >= 1 && channels <= 4, SVAE_EINVAL, "bad image shape");
     return rotate_bicubic(src, dst, inv_affine, mode, B, n_rows, n_cols, channels, quantize_u8, (cudaStream_t)stream);
+}
+
+// Python's round(x, 15): correctly rounded decimal -> nearest double (glibc printf/strtod are exact)
+static double round15(double x) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.15f", x);
+    return strtod(buf, nullptr);
+}
+
+int svae_rotation_matrices(const double* angles_deg, int B, int n_rows, int n_cols, double* inv_affine, int32_t* mode) {
+    SVAE_REQUIRE(angles_deg && inv_affine && mode && B >= 0, SVAE_EINVAL, "null argument");
+    const double cx = n_cols / 2.0, cy = n_rows / 2.0;
+    for (int b = 0; b < B; ++b) {
+        double ang = fmod(angles_deg[b], 360.0);              // Python's float %: result takes the divisor's sign
+        if (ang < 0.0) ang += 360.0;
+        double* m = inv_affine + (size_t)b * 6;
+        mode[b] = 0;
+        if (ang == 0.0) mode[b] = 1;
+        else if (ang == 180.0) mode[b] = 2;
+        else if (n_rows == n_cols && ang == 90.0) mode[b] = 3;
+        else if (n_rows == n_cols && ang == 270.0) mode[b] = 4;
+        const double a = -(ang * (M_PI / 180.0));               // -math.radians(angle)
+        m[0] = round15(cos(a)); m[1] = round15(sin(a)); m[3] = round15(-sin(a)); m[4] = round15(cos(a));
+        m[2] = (m[0] * -cx + m[1] * -cy + 0.0) + cx;            // transform(-cx, -cy) + centre  (PIL/Image.py)
+        m[5] = (m[3] * -cx + m[4] * -cy + 0.0) + cy;
+    }
+    return SVAE_OK;
 }
 
 int svae_sm_clock_probe(float* out_mhz, void* stream) {

@@ -432,32 +432,18 @@ def rotate_bicubic(y: torch.Tensor, n_rows: int, n_cols: int, angles_deg, channe
     """Rotate every image of the minibatch y (B, n_rows*n_cols[, channels]) counter-clockwise by its angle
     (degrees), on the device, with the arithmetic of Pillow's Image.rotate(angle, resample=BICUBIC) -- what the
     reference does per image on the host for --augment-rotation (train_particles.py:39-43, train_galaxy.py:47-54).
-    The destination->source affine matrices are built here exactly as PIL/Image.py builds them."""
+    The destination->source affine matrices come from svae_rotation_matrices (host helper of the library), which
+    builds them exactly as PIL/Image.py does."""
     _require_cuda(y)
     B = y.shape[0]
-    import numpy as np
-    ang = [float(a) % 360.0 for a in angles_deg]
-    # Pillow: angle = -radians(angle); matrix = [round(cos,15), round(sin,15), 0, round(-sin,15), round(cos,15), 0]
-    # (math.cos/sin, not numpy's vectorised versions, so the 15-digit rounding sees the same bits as Pillow does)
-    rad = [-math.radians(a) for a in ang]
-    c = np.array([round(math.cos(r), 15) for r in rad], dtype=np.float64)
-    sn = np.array([round(math.sin(r), 15) for r in rad], dtype=np.float64)
-    cx, cy = n_cols / 2, n_rows / 2
-    m = np.zeros((B, 6), dtype=np.float64)
-    m[:, 0], m[:, 1], m[:, 3], m[:, 4] = c, sn, -sn, c
-    m[:, 2] = (m[:, 0] * -cx + m[:, 1] * -cy + 0.0) + cx
-    m[:, 5] = (m[:, 3] * -cx + m[:, 4] * -cy + 0.0) + cy
-    a = np.array(ang)
-    md = np.zeros(B, dtype=np.int32)           # Pillow's fast paths: copy, ROTATE_180, ROTATE_90, ROTATE_270
-    md[a == 0] = 1
-    md[a == 180] = 2
-    if n_rows == n_cols:
-        md[a == 90] = 3
-        md[a == 270] = 4
-    mats, modes = torch.from_numpy(m), torch.from_numpy(md)
+    ang = torch.as_tensor(angles_deg, dtype=torch.float64).contiguous()
+    mats = torch.empty(B, 6, dtype=torch.float64).pin_memory()
+    modes = torch.empty(B, dtype=torch.int32).pin_memory()
+    L.check(L.lib.svae_rotation_matrices(ang.data_ptr(), B, n_rows, n_cols, mats.data_ptr(), modes.data_ptr()),
+            "svae_rotation_matrices")
     src = _f32(y)
     out = torch.empty_like(src)
-    mats_d, modes_d = mats.to(y.device), modes.to(y.device)
+    mats_d, modes_d = mats.to(y.device, non_blocking=True), modes.to(y.device, non_blocking=True)
     L.check(L.lib.svae_rotate_bicubic(src.data_ptr(), out.data_ptr(), mats_d.data_ptr(), modes_d.data_ptr(), B, n_rows,
                                       n_cols, channels, int(quantize_u8), _stream()), "svae_rotate_bicubic")
     return out.view_as(y)

@@ -98,3 +98,22 @@ def test_unsupported_options_raise(built):
         p = M.SpatialGenerator(3, 16, resid=True, num_layers=2)
     with pytest.raises(NotImplementedError):
         p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
+
+
+def test_rotation_matrices_match_pillow_recipe(built):
+    """svae_rotation_matrices is host code: compare with the PIL/Image.py recipe restated in the oracle."""
+    import ctypes as C
+    import numpy as np
+    from oracle.pillow_rotate import rotate_matrix
+    rng = np.random.default_rng(0)
+    ang = np.concatenate([rng.uniform(-720, 720, 200), [0.0, 90.0, 180.0, 270.0, 360.0, -90.0]])
+    B = len(ang)
+    mats = np.zeros((B, 6))
+    modes = np.zeros(B, dtype=np.int32)
+    rc = built.lib.svae_rotation_matrices(ang.ctypes.data, B, 40, 40, mats.ctypes.data, modes.ctypes.data)
+    assert rc == 0
+    for b in range(B):
+        a = ang[b] % 360.0
+        expect_mode = {0.0: 1, 180.0: 2, 90.0: 3, 270.0: 4}.get(a, 0)
+        assert modes[b] == expect_mode
+        assert mats[b].tolist() == rotate_matrix(ang[b], 40, 40), (ang[b], mats[b], rotate_matrix(ang[b], 40, 40))
