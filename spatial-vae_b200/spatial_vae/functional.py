@@ -427,6 +427,9 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_rot_staging = {}
+
+
 def rotate_bicubic(y: torch.Tensor, n_rows: int, n_cols: int, angles_deg, channels: int = 1,
                    quantize_u8: bool = False) -> torch.Tensor:
     """Rotate every image of the minibatch y (B, n_rows*n_cols[, channels]) counter-clockwise by its angle
@@ -437,13 +440,20 @@ def rotate_bicubic(y: torch.Tensor, n_rows: int, n_cols: int, angles_deg, channe
     _require_cuda(y)
     B = y.shape[0]
     ang = torch.as_tensor(angles_deg, dtype=torch.float64).contiguous()
-    mats = torch.empty(B, 6, dtype=torch.float64).pin_memory()
-    modes = torch.empty(B, dtype=torch.int32).pin_memory()
+    # a small ring of pinned staging buffers per batch size: the async copies of earlier calls may still be
+    # queued behind GPU work while the host already fills the next set
+    slot = _rot_staging.setdefault(B, {"i": 0, "bufs": [(torch.empty(B, 6, dtype=torch.float64).pin_memory(),
+                                                         torch.empty(B, dtype=torch.int32).pin_memory(),
+                                                         torch.cuda.Event()) for _ in range(8)]})
+    slot["i"] = (slot["i"] + 1) % 8
+    mats, modes, ev = slot["bufs"][slot["i"]]
+    ev.synchronize()          # the copy that last used this set has finished (no-op on first use)
     L.check(L.lib.svae_rotation_matrices(ang.data_ptr(), B, n_rows, n_cols, mats.data_ptr(), modes.data_ptr()),
             "svae_rotation_matrices")
     src = _f32(y)
     out = torch.empty_like(src)
     mats_d, modes_d = mats.to(y.device, non_blocking=True), modes.to(y.device, non_blocking=True)
+    ev.record()
     L.check(L.lib.svae_rotate_bicubic(src.data_ptr(), out.data_ptr(), mats_d.data_ptr(), modes_d.data_ptr(), B, n_rows,
                                       n_cols, channels, int(quantize_u8), _stream()), "svae_rotate_bicubic")
     return out.view_as(y)
