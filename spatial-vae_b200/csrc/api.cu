@@ -133,6 +133,11 @@ static int encoder_head_forward(const SvaeShape& s, const SvaeEncoderParams& q, 
     a.C = out; a.ldc = 2 * s.I;
     a.M = s.B; a.N = 2 * s.I; a.K = s.Hq;
     a.bias = q.b[s.Lq];
+    // narrow output (2I columns): few tiles walking a long K are latency bound -> spread K over 4x the CTAs
+    if (s.Hq >= 256 && (long)s.B * 2 * s.I <= (1L << 20)) {
+        SVAE_CUDA(cudaMemsetAsync(out, 0, (size_t)s.B * 2 * s.I * sizeof(float), st));
+        a.split_k = 4;
+    }
     return sgemm(a, st);
 }
 
@@ -450,6 +455,10 @@ static int first_layer_param_grads(const SvaeShape& s, const SvaeConfig& c, cons
             x.C = dz; x.ldc = s.Z;
             x.M = s.B; x.N = s.Z; x.K = s.H;
             x.alpha = z_scale;
+            if (s.H >= 256) {      // narrow output, long K: split-K (see encoder_head_forward)
+                SVAE_CUDA(cudaMemsetAsync(dz, 0, (size_t)s.B * s.Z * sizeof(float), st));
+                x.split_k = 4;
+            }
             SVAE_TRY(sgemm(x, st));
         }
     }

@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) out_backward_v8_k(const T* __restrict__ h
             }
         }
         if (active) {
-#pragma unroll 2
+#pragma unroll 4
             for (int r = rl; r < nrows; r += lanes) {
                 float hv[8], dv[8];
                 load8(h + (r0 + r) * Hp + g * 8, hv);
@@ -680,9 +680,65 @@ __global__ void __launch_bounds__(256) image_col_reduce_k(const T* __restrict__ 
         Sb[2 * Hp + pr * 2] = m10; Sb[2 * Hp + pr * 2 + 1] = m11;
     }
 }
+
+// Wide variant (Hp % 8 == 0, Hp <= 2048): thread = (8-column group, row lane), 16-byte loads, several rows in
+// flight per thread; row lanes are combined through shared memory.  One block per image.
+template <typename T>
+__global__ void __launch_bounds__(256) image_col_reduce_v8_k(const T* __restrict__ d0, int b0, int P, int Hp,
+                                                             const float* __restrict__ grid,
+                                                             const float* __restrict__ xe, float* __restrict__ S) {
+    extern __shared__ float red[];            // lanes x 3 x Hp
+    const int bl = blockIdx.x, b = b0 + bl;
+    const float* coords = xe ? xe + (long)b * P * 2 : grid;
+    const T* base = d0 + (long)bl * P * Hp;
+    const int groups = Hp >> 3;
+    const int lanes = max(1, 256 / groups);
+    const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+    float s[8], m0[8], m1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; m0[e] = 0.f; m1[e] = 0.f; }
+    if (rl < lanes) {
+#pragma unroll 4
+        for (int p = rl; p < P; p += lanes) {
+            float v[8];
+            load8(base + (long)p * Hp + g * 8, v);
+            const float2 c = __ldg(reinterpret_cast<const float2*>(coords) + p);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += v[e];
+                m0[e] = fmaf(c.x, v[e], m0[e]);
+                m1[e] = fmaf(c.y, v[e], m1[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            red[(rl * 3 + 0) * Hp + g * 8 + e] = s[e];
+            red[(rl * 3 + 1) * Hp + g * 8 + e] = m0[e];
+            red[(rl * 3 + 2) * Hp + g * 8 + e] = m1[e];
+        }
+    }
+    __syncthreads();
+    float* Sb = S + (long)b * 3 * Hp;
+    for (int i = threadIdx.x; i < 3 * Hp; i += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[l * 3 * Hp + i];
+        Sb[i] = t;
+    }
+}
+
 template <typename T>
 int image_col_reduce(const T* delta0, int b0, int nb, int P, int Hp, const float* grid, const float* x_explicit,
                      float* S, cudaStream_t st) {
+    if ((Hp & 7) == 0 && Hp <= 2048) {
+        const int groups = Hp >> 3;
+        const int lanes = groups >= 256 ? 1 : 256 / groups;
+        const size_t smem = (size_t)lanes * 3 * Hp * sizeof(float);
+        if (smem <= 48 * 1024) {
+            image_col_reduce_v8_k<T><<<nb, 256, smem, st>>>(delta0, b0, P, Hp, grid, x_explicit, S);
+            SVAE_LAUNCH_CHECK();
+            return SVAE_OK;
+        }
+    }
     dim3 g(nb, ceil_div(Hp / 2, 256));
     image_col_reduce_k<T><<<g, 256, 0, st>>>(delta0, b0, P, Hp, grid, x_explicit, S);
     SVAE_LAUNCH_CHECK();
