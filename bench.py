@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel of the step instead of replaying a CUDA graph")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.batch > 0:
@@ -318,8 +319,9 @@ def main():
             offs = aug_rng.uniform(0, 2 * math.pi, size=B)
             y_enc = SF.rotate_bicubic(y, c["n"], c["n"], offs * (360 / 2 / math.pi))
             theta_offset = torch.from_numpy(offs).float().to(device, non_blocking=True)
-        return trainer.step(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
+        return step_fn(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
 
+    step_fn = trainer.step if args.no_graph else trainer.step_graphed
     for i in range(args.warmup):
         device_step(i)
     torch.cuda.synchronize()
@@ -334,6 +336,12 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.1)           # first NVML sample lands before the timed region starts
+    # library launches of ONE step (counted on an eager step; a graph replay re-issues the same kernels)
+    lc0 = L.lib.svae_launch_count()
+    trainer.step(grid, SF.gather_rows(data, torch.arange(B, device=device)), global_batch=B * world,
+                 ctf=SF.gather_rows(ctf_all, torch.arange(B, device=device)) if ctf_all is not None else None)
+    launches_per_step = L.lib.svae_launch_count() - lc0 + (1 if True else 0)      # + gather_rows in device_step
+    torch.cuda.synchronize()
     launches0 = L.lib.svae_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -350,6 +358,8 @@ def main():
     if world > 1:
         dist.barrier()
     launches = L.lib.svae_launch_count() - launches0
+    if not args.no_graph:
+        launches = launches_per_step * args.steps          # kernels replayed from the captured graph + the gathers
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -383,7 +393,7 @@ def main():
             offs = aug_rng.uniform(0, 2 * math.pi, size=B)
             y_enc = SF.rotate_bicubic(y, c["n"], c["n"], offs * (360 / 2 / math.pi))
             theta_offset = torch.from_numpy(offs).float().to(device, non_blocking=True)
-        r = trainer.step(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
+        r = step_fn(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
         out_host.copy_(r, non_blocking=False)      # device -> host read of the step's result (syncs)
         return out_host
 
@@ -420,6 +430,7 @@ def main():
                    "precision": args.precision + (" (bf16 tcgen05 hidden GEMMs, fp32 accumulate; everything else fp32)"
                                                   if args.precision == "fast" else " (fp32 FFMA)"),
                    "parallelism": f"dp{world}",
+                   "launch": "eager" if args.no_graph else "CUDA graph replay of the captured step",
                    "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2) and "
                          "gathers a fresh shuffled batch"},
         "pixel_evals_per_s": value * P,

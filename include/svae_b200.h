@@ -166,6 +166,14 @@ int  svae_step(const SvaeShape* shape, const SvaeConfig* cfg,
 int  svae_adam_step(float* param, float* grad, float* m, float* v, size_t n,
                     float lr, float beta1, float beta2, float eps, int t, int zero_grad, void* stream);
 
+/* Adam for CUDA-graph replays.  svae_adam_tick increments the device-resident step counter *t_dev and writes the
+ * step's bias corrections {1 - beta1^t, sqrt(1 - beta2^t)} to bias_corr_dev (2 floats, device);
+ * svae_adam_step_graph is svae_adam_step reading those scalars from device memory, so a captured
+ * tick + step pair can be replayed any number of times without host-side state. */
+int  svae_adam_tick(int32_t* t_dev, float* bias_corr_dev, float beta1, float beta2, void* stream);
+int  svae_adam_step_graph(float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                          float eps, const float* bias_corr_dev, int zero_grad, void* stream);
+
 /* dst[i, :] = src[index[i], :] for i < n_rows: one launch replaces the per-sample DataLoader fetch. */
 int  svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
                       void* stream);

@@ -673,7 +673,18 @@ int svae_adam_step(float* param, float* grad, float* m, float* v, size_t n, floa
                    float eps, int t, int zero_grad, void* stream) {
     SVAE_REQUIRE(param && grad && m && v, SVAE_EINVAL, "null argument");
     SVAE_REQUIRE(t >= 1, SVAE_EINVAL, "Adam step count starts at 1");
-    return adam(param, grad, m, v, n, lr, beta1, beta2, eps, t, zero_grad, (cudaStream_t)stream);
+    return adam(param, grad, m, v, n, lr, beta1, beta2, eps, t, zero_grad, nullptr, (cudaStream_t)stream);
+}
+
+int svae_adam_tick(int32_t* t_dev, float* bias_corr_dev, float beta1, float beta2, void* stream) {
+    SVAE_REQUIRE(t_dev && bias_corr_dev, SVAE_EINVAL, "null argument");
+    return adam_tick(t_dev, bias_corr_dev, beta1, beta2, (cudaStream_t)stream);
+}
+
+int svae_adam_step_graph(float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                         float eps, const float* bias_corr_dev, int zero_grad, void* stream) {
+    SVAE_REQUIRE(param && grad && m && v && bias_corr_dev, SVAE_EINVAL, "null argument");
+    return adam(param, grad, m, v, n, lr, beta1, beta2, eps, 0, zero_grad, bias_corr_dev, (cudaStream_t)stream);
 }
 
 int svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,

@@ -65,8 +65,10 @@ int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int
                     const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
                     cudaStream_t st);
 
+int adam_tick(int* t_dev, float* bias_corr_dev, float b1, float b2, cudaStream_t st);
+// bias_corr_dev: optional device pointer to {1 - b1^t, sqrt(1 - b2^t)}; when set it overrides t
 int adam(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, int t,
-         int zero_grad, cudaStream_t st);
+         int zero_grad, const float* bias_corr_dev, cudaStream_t st);
 int gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int64_t row_len, cudaStream_t st);
 // dst (rows_p x cols_p, bf16, zero padded) = src (rows x cols fp32)
 int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p, cudaStream_t st);

@@ -856,7 +856,9 @@ int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int
 // Adam (torch.optim.Adam, train_mnist.py:389-392,149-150), gather, fp32 -> padded bf16
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       size_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, int zero_grad) {
+                       size_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, int zero_grad,
+                       const float* __restrict__ bc_dev) {
+    if (bc_dev != nullptr) { bc1 = bc_dev[0]; bc2_sqrt = bc_dev[1]; }   // CUDA-graph replays: step-dependent scalars live in memory
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float gi = g[i];
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -867,12 +869,24 @@ __global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __re
         if (zero_grad) g[i] = 0.f;
     }
 }
+// device-resident step counter: t += 1, then the bias corrections of step t (double precision, like the host path)
+__global__ void adam_tick_k(int* t_dev, float* bc, float b1, float b2) {
+    const int t = ++(*t_dev);
+    bc[0] = (float)(1.0 - pow((double)b1, (double)t));
+    bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
+int adam_tick(int* t_dev, float* bias_corr_dev, float b1, float b2, cudaStream_t st) {
+    adam_tick_k<<<1, 1, 0, st>>>(t_dev, bias_corr_dev, b1, b2);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
 int adam(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, int t,
-         int zero_grad, cudaStream_t st) {
+         int zero_grad, const float* bias_corr_dev, cudaStream_t st) {
     if (n == 0) return SVAE_OK;
-    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+    const double bc1 = 1.0 - pow((double)b1, t > 0 ? t : 1), bc2 = 1.0 - pow((double)b2, t > 0 ? t : 1);
     const int blocks = (int)min((size_t)148 * 16, (n + 255) / 256);
-    adam_k<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), zero_grad);
+    adam_k<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), zero_grad, bias_corr_dev);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }

@@ -24,7 +24,7 @@ PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST}
 EXPORTS = [
     "svae_version", "svae_last_error", "svae_launch_count", "svae_device_sm_count", "svae_workspace_bytes",
     "svae_encoder_forward", "svae_encoder_backward", "svae_decoder_forward", "svae_decoder_backward",
-    "svae_step", "svae_adam_step", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_sm_clock_probe", "svae_gemm_bf16",
+    "svae_step", "svae_adam_step", "svae_adam_tick", "svae_adam_step_graph", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_sm_clock_probe", "svae_gemm_bf16",
 ]
 
 
@@ -81,6 +81,8 @@ def _load():
                               P(SvaeStepInputs), P(SvaeStepOutputs), P(SvaeDecoderParams), P(SvaeEncoderParams),
                               vp, sz, vp]
     lib.svae_adam_step.argtypes = [vp, vp, vp, vp, sz, f32, f32, f32, f32, i32, i32, vp]
+    lib.svae_adam_tick.argtypes = [vp, vp, f32, f32, vp]
+    lib.svae_adam_step_graph.argtypes = [vp, vp, vp, vp, sz, f32, f32, f32, f32, vp, i32, vp]
     lib.svae_gather_rows.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.svae_rotation_matrices.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.svae_rotate_bicubic.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]

@@ -416,12 +416,24 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch
                                  lr, betas[0], betas[1], eps, t, int(zero_grad), _stream()), "svae_adam_step")
 
 
-def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+def adam_step_graph(param, grad, m, v, lr, t_dev, bias_corr_dev, betas=(0.9, 0.999), eps=1e-8, zero_grad=True) -> None:
+    """adam_step driven by a device-resident step counter (t_dev int32[1] is incremented, the bias corrections
+    go to bias_corr_dev float32[2]): no host-side state, so the pair can be captured in a CUDA graph."""
+    _require_cuda(param, grad, m, v, t_dev, bias_corr_dev)
+    L.check(L.lib.svae_adam_tick(t_dev.data_ptr(), bias_corr_dev.data_ptr(), betas[0], betas[1], _stream()),
+            "svae_adam_tick")
+    L.check(L.lib.svae_adam_step_graph(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(),
+                                       lr, betas[0], betas[1], eps, bias_corr_dev.data_ptr(), int(zero_grad),
+                                       _stream()), "svae_adam_step_graph")
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """src[index] for a 2-D+ fp32 dataset resident on the GPU (replaces the per-sample DataLoader fetch)."""
     _require_cuda(src, index)
     src2 = src.reshape(src.shape[0], -1)
     idx = index.to(torch.int64).contiguous()
-    out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
     L.check(L.lib.svae_gather_rows(src2.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), src2.shape[1],
                                    _stream()), "svae_gather_rows")
     return out

@@ -65,7 +65,11 @@ class Trainer:
         self.p_net, self.q_net, self.spec = p_net, q_net, spec
         self.lr, self.betas, self.adam_eps = lr, betas, eps
         self.flat = FlatParams(list(p_net.parameters()) + list(q_net.parameters()))
-        self.t = 0
+        self.t = 0                                  # host mirror of the device-resident Adam step counter
+        dev = self.flat.data.device
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._graphs = {}
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -104,8 +108,70 @@ class Trainer:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
         self.t += 1
-        SF.adam_step(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t, self.betas,
-                     self.adam_eps, zero_grad=True)
+        SF.adam_step_graph(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t_dev, self.bc_dev,
+                           self.betas, self.adam_eps, zero_grad=True)
+        means = sums / max(B_global, 1)
+        return torch.stack([means[2], means[0], means[1]])
+
+    # -- the same step replayed from a CUDA graph ------------------------------------------------------
+    def step_graphed(self, x_coord: torch.Tensor, y_local: torch.Tensor, *, global_batch: Optional[int] = None,
+                     ctf=None, mask=None, y_enc=None, theta_offset=None, z_scale: Optional[float] = None) -> torch.Tensor:
+        """`step` with the ~40 kernel launches (+ the NCCL allreduce) of one train step captured once per input
+        shape into a CUDA graph and replayed: the inputs are copied into static buffers, eps is drawn inside the
+        graph, Adam's step counter and bias corrections live in device memory.  The first call for a
+        shape runs one ordinary eager step (lazy initialisation must not happen under capture) and captures on the
+        second.  Returns the same [elbo, logp, kl] tensor (a static buffer: copy it if you keep it)."""
+        B_local = y_local.shape[0]
+        B_global = global_batch if global_batch is not None else B_local * self.world
+        key = (tuple(y_local.shape), B_global, None if ctf is None else tuple(ctf.shape), mask is not None,
+               y_enc is not None, theta_offset is not None, z_scale)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "warm"
+            return self.step(x_coord, y_local, global_batch=global_batch, ctf=ctf, mask=mask, y_enc=y_enc,
+                             theta_offset=theta_offset, z_scale=z_scale)
+        if entry == "warm":
+            st = {"y": y_local.clone(), "ctf": ctf.clone() if ctf is not None else None,
+                  "y_enc": y_enc.clone() if y_enc is not None else None,
+                  "toff": theta_offset.clone() if theta_offset is not None else None}
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._step_body(x_coord, st["y"], B_global, None, st["y_enc"], st["toff"], st["ctf"], mask,
+                                            z_scale)
+            st["graph"] = graph
+            self._graphs[key] = entry = st
+            # the capture itself did not execute anything
+        st = entry
+        st["y"].copy_(y_local, non_blocking=True)
+        if ctf is not None:
+            st["ctf"].copy_(ctf, non_blocking=True)
+        if y_enc is not None:
+            st["y_enc"].copy_(y_enc, non_blocking=True)
+        if theta_offset is not None:
+            st["toff"].copy_(theta_offset, non_blocking=True)
+        self.t += 1
+        st["graph"].replay()
+        return st["out"]
+
+    def _step_body(self, x_coord, y_local, B_global, eps, y_enc, theta_offset, ctf, mask, z_scale):
+        """Everything of one train step that is enqueued on the stream (shared by step_graphed's capture)."""
+        B_local = y_local.shape[0]
+        spec = self.spec
+        if z_scale is not None and z_scale != spec.z_scale:
+            spec = SF.StepSpec(**{**spec.__dict__, "z_scale": z_scale})
+        I = self.enc[-1][0].shape[0] // 2
+        if eps is None:
+            eps = torch.empty(B_local, I, dtype=torch.float32, device=y_local.device).normal_()
+        stats, _, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc,
+                                  theta_offset=theta_offset, ctf=ctf, mask=mask, grad_dec=self.gdec,
+                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1))
+        sums = stats.sum(0) if B_local > 0 else stats.new_zeros(3)
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+        SF.adam_step_graph(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t_dev, self.bc_dev,
+                           self.betas, self.adam_eps, zero_grad=True)
         means = sums / max(B_global, 1)
         return torch.stack([means[2], means[0], means[1]])
 

@@ -50,7 +50,9 @@ def _install_doubles(SF):
         stats = torch.stack([out["logp_i"], out["kl_i"], out["logp_i"] - out["kl_i"]], 1)
         return stats, None, None
 
-    def fake_adam(param, grad, m, v, lr, t, betas=(0.9, 0.999), eps=1e-8, zero_grad=True):
+    def fake_adam(param, grad, m, v, lr, t_dev, bc_dev, betas=(0.9, 0.999), eps=1e-8, zero_grad=True):
+        t_dev += 1                       # the device-resident step counter of svae_adam_tick
+        t = int(t_dev)
         m.mul_(betas[0]).add_(grad, alpha=1 - betas[0])
         v.mul_(betas[1]).addcmul_(grad, grad, value=1 - betas[1])
         bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
@@ -59,7 +61,7 @@ def _install_doubles(SF):
             grad.zero_()
 
     SF.run_step = fake_run_step
-    SF.adam_step = fake_adam
+    SF.adam_step_graph = fake_adam
 
 
 def _worker(rank, world, port, batches, tmp):
