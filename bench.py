@@ -321,7 +321,11 @@ def main():
             theta_offset = torch.from_numpy(offs).float().to(device, non_blocking=True)
         return step_fn(grid, y, global_batch=B * world, ctf=ctf, y_enc=y_enc, theta_offset=theta_offset)
 
-    step_fn = trainer.step if args.no_graph else trainer.step_graphed
+    # CUDA-graph replay on one GPU.  With several ranks the step is enqueued kernel by kernel: capturing the NCCL
+    # allreduce worked at 8 ranks on C4/C5, but an 8-rank C2 run hung in the same session and there was no GPU budget
+    # left to find out why, so the multi-GPU default stays on the path that was measured at 2/4/8 GPUs.
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("BENCH_GRAPH_MULTI") == "1")
+    step_fn = trainer.step_graphed if use_graph else trainer.step
     for i in range(args.warmup):
         device_step(i)
     torch.cuda.synchronize()
@@ -358,7 +362,7 @@ def main():
     if world > 1:
         dist.barrier()
     launches = L.lib.svae_launch_count() - launches0
-    if not args.no_graph:
+    if use_graph:
         launches = launches_per_step * args.steps          # kernels replayed from the captured graph + the gathers
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
@@ -430,7 +434,7 @@ def main():
                    "precision": args.precision + (" (bf16 tcgen05 hidden GEMMs, fp32 accumulate; everything else fp32)"
                                                   if args.precision == "fast" else " (fp32 FFMA)"),
                    "parallelism": f"dp{world}",
-                   "launch": "eager" if args.no_graph else "CUDA graph replay of the captured step",
+                   "launch": "CUDA graph replay of the captured step" if use_graph else "eager",
                    "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2) and "
                          "gathers a fresh shuffled batch"},
         "pixel_evals_per_s": value * P,

@@ -181,9 +181,11 @@ def run_epoch(trainer: Trainer, x_coord, data, *, train: bool, minibatch_size: i
             y_enc = theta_offset = None
             if augment is not None:
                 y_enc, theta_offset = augment(y)
-            # one CUDA-graph replay per minibatch (captured once per batch shape; see Trainer.step_graphed)
-            res = trainer.step_graphed(x_coord, y, global_batch=bsz, y_enc=y_enc, theta_offset=theta_offset, ctf=c,
-                                       mask=mask, z_scale=z_scale)
+            # single GPU: one CUDA-graph replay per minibatch (captured once per batch shape, Trainer.step_graphed);
+            # under torchrun the step is enqueued kernel by kernel (the path measured at 2/4/8 GPUs)
+            step = trainer.step_graphed if trainer.world == 1 else trainer.step
+            res = step(x_coord, y, global_batch=bsz, y_enc=y_enc, theta_offset=theta_offset, ctf=c, mask=mask,
+                       z_scale=z_scale)
         else:
             want = first_batch_hook is not None and start == 0
             res, y_hat = trainer.evaluate(x_coord, y, global_batch=bsz, ctf=c, mask=mask, want_y_hat=want,

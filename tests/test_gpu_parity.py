@@ -443,6 +443,13 @@ def test_particle_configs_at_full_model_size_against_oracle(cfgname, B):
         assert rel.max() <= tol, f"{cfgname} {precision}: {rel.max():.2e}"
 
 
+# The two tests below were written after the round's GPU budget was spent and have not run on hardware yet:
+# they are skipped unless SVAE_RUN_UNVALIDATED=1 so the suite only contains checks that were seen green on a B200.
+_unvalidated = pytest.mark.skipif(__import__("os").environ.get("SVAE_RUN_UNVALIDATED") != "1",
+                                  reason="not yet run on a GPU (added after the round's GPU budget was exhausted)")
+
+
+@_unvalidated
 @pytest.mark.parametrize("precision", ["parity", "fast"])
 def test_softplus_output_channel_matches_oracle(precision):
     """--softplus (models.py:129-130): softplus on output channel 0 AFTER the sigmoid, with and without fit-noise."""
@@ -460,6 +467,7 @@ def test_softplus_output_channel_matches_oracle(precision):
             assert float((g - r).abs().max()) <= gtol * scale, f"C={C} grad {i}"
 
 
+@_unvalidated
 def test_activation_variants_match_oracle():
     """ReLU and sigmoid hidden activations (train_galaxy.py:426-434) in both precisions."""
     for act in ("relu", "sigmoid"):
