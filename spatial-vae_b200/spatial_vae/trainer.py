@@ -140,6 +140,9 @@ class Trainer:
                 st["out"] = self._step_body(x_coord, st["y"], B_global, None, st["y_enc"], st["toff"], st["ctf"], mask,
                                             z_scale)
             st["graph"] = graph
+            # the captured kernels hold raw pointers into the library workspace: keep that buffer alive even if a
+            # later, larger request makes spatial_vae.functional.workspace() allocate a new one
+            st["keepalive"] = list(SF._workspaces.values())
             self._graphs[key] = entry = st
             # the capture itself did not execute anything
         st = entry

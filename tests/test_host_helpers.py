@@ -77,3 +77,29 @@ def test_activation_flag_quirks():
     assert D.activation_from_flag("relu", "mnist") is nn.LeakyReLU      # reference train_mnist.py:344-348
     assert D.activation_from_flag("relu", "galaxy") is nn.ReLU          # reference train_galaxy.py:431-432
     assert D.activation_from_flag("leakyrelu", "galaxy") is nn.Tanh     # typo at train_galaxy.py:429
+
+
+def test_bench_flop_model_matches_survey_table():
+    """bench.py's algorithmic FLOPs per image per train step against SURVEY.md section 8(d)
+    (C1 1.187, C2 1.188, C3 2.426, C4 74.371, C5 2.430 GFLOP): the roofline fractions rest on these."""
+    sys.path.insert(0, os.path.dirname(PKG))
+    import bench
+    expect = {"c1": 1.187e9, "c2": 1.188e9, "c3": 2.426e9, "c4": 74.371e9, "c5": 2.430e9}
+    for name, gf in expect.items():
+        got = bench.flops_per_image_train(bench.CONFIGS[name])
+        assert abs(got - gf) / gf < 2e-3, (name, got, gf)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU port of the reference step) needs no GPU and prints the contract's line."""
+    import json
+    import subprocess
+    root = os.path.dirname(PKG)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c1",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
