@@ -451,8 +451,15 @@ def main():
         kt = time_gemm_kernels(c, rows, device)
         alg = 2.0 * rows * c["H"] * c["H"]
         dom = max(kt, key=kt.get)
+        # DRAM bytes per launch (read + write) of the three GEMMs from the committed `ncu --set full` capture
+        # (profiles/r01_v3_summary.md), which was taken at exactly this row count and width; null for other shapes
+        traffic = None
+        if rows == 1024 * 784 and c["H"] == 500:
+            traffic = {"fwd": 0.822635e9 + 0.777726e9, "dx": 1.644998e9 + 0.791843e9, "dw": 1.645260e9 + 0.004575e9}[dom]
         line["roofline"] = {"bound": "tensor", "kernel": f"tc_gemm_kernel<{dom}>", "achieved": alg / kt[dom] / 1e12,
-                            "peak": burst, "unit": "TFLOP/s", "frac": alg / kt[dom] / 1e12 / burst, "traffic": None,
+                            "peak": burst, "unit": "TFLOP/s", "frac": alg / kt[dom] / 1e12 / burst, "traffic": traffic,
+                            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                              "profiles/r01_v3_summary.md" if traffic else None,
                             "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst), {src}",
                             "all_kernels_tflops": {k: alg / v / 1e12 for k, v in kt.items()},
                             "all_kernels_ms": {k: v * 1e3 for k, v in kt.items()}}
