@@ -344,7 +344,7 @@ def main():
     lc0 = L.lib.svae_launch_count()
     trainer.step(grid, SF.gather_rows(data, torch.arange(B, device=device)), global_batch=B * world,
                  ctf=SF.gather_rows(ctf_all, torch.arange(B, device=device)) if ctf_all is not None else None)
-    launches_per_step = L.lib.svae_launch_count() - lc0 + (1 if True else 0)      # + gather_rows in device_step
+    launches_per_step = L.lib.svae_launch_count() - lc0        # 2 gathers + the step's kernels + Adam
     torch.cuda.synchronize()
     launches0 = L.lib.svae_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
