@@ -59,6 +59,7 @@ class StepConfig:
     z_scale: float = 1.0
     activation: str = "tanh"
     softplus: bool = False
+    resid: bool = False          # --resid: ResidLinear hidden layers in both networks (train_particles.py:291,437)
 
 
 def act_fn(name: str):
@@ -77,28 +78,42 @@ def act_fn(name: str):
 # parameters as plain dictionaries of tensors
 # --------------------------------------------------------------------------------------
 
-def decoder_params_from_state(sd: Dict[str, torch.Tensor]) -> Dict[str, object]:
-    """state_dict of a SpatialGenerator (non-resid, non-bilinear) -> plain dict.
+def _linear_keys(sd, prefix="layers."):
+    """(index, weight key, bias key) of every Linear inside a Sequential, plain or wrapped in ResidLinear
+    (``layers.N.weight`` vs ``layers.N.linear.weight``, models.py:13-21,79-83)."""
+    out = []
+    for k in sd:
+        if k.startswith(prefix) and k.endswith(".weight"):
+            out.append((int(k.split(".")[1]), k, k[:-len("weight")] + "bias"))
+    return sorted(out)
 
-    Key layout follows models.py:69-87: ``coord_linear``, ``latent_linear``, and the
-    Sequential ``layers`` = [act, (Linear, act)*(L-1), Linear, Sigmoid] so hidden Linears sit
-    at odd indices 1,3,... and the output Linear is the last odd index.
+
+def decoder_params_from_state(sd: Dict[str, torch.Tensor]) -> Dict[str, object]:
+    """state_dict of a SpatialGenerator -> plain dict.
+
+    Key layout follows models.py:69-87: ``coord_linear``, ``latent_linear``, optional ``bilinear`` and the
+    Sequential ``layers`` = [act, (Linear, act)*(L-1) | ResidLinear*(L-1), Linear, Sigmoid]; ``resid`` is True when
+    the hidden layers are ResidLinear modules.
     """
-    idx = sorted({int(k.split(".")[1]) for k in sd if k.startswith("layers.") and k.endswith(".weight")})
-    hidden = [(sd[f"layers.{i}.weight"], sd[f"layers.{i}.bias"]) for i in idx[:-1]]
+    lin = _linear_keys(sd)
+    hidden = [(sd[w], sd[b]) for _, w, b in lin[:-1]]
     out = {
         "coord_w": sd["coord_linear.weight"], "coord_b": sd["coord_linear.bias"],
         "latent_w": sd.get("latent_linear.weight"),
         "hidden": hidden,
-        "out_w": sd[f"layers.{idx[-1]}.weight"], "out_b": sd[f"layers.{idx[-1]}.bias"],
+        "out_w": sd[lin[-1][1]], "out_b": sd[lin[-1][2]],
     }
+    if "bilinear.weight" in sd:
+        out["bilinear_w"] = sd["bilinear.weight"]           # (H, coord features, Z)
+    if any(".linear." in w for _, w, _ in lin):
+        out["resid"] = True
     return out
 
 
 def encoder_params_from_state(sd: Dict[str, torch.Tensor]) -> List[Tuple[torch.Tensor, torch.Tensor]]:
-    """state_dict of an InferenceNetwork -> [(W, b)] in application order (models.py:31-43)."""
-    idx = sorted({int(k.split(".")[1]) for k in sd if k.endswith(".weight")})
-    return [(sd[f"layers.{i}.weight"], sd[f"layers.{i}.bias"]) for i in idx]
+    """state_dict of an InferenceNetwork -> [(W, b)] in application order (models.py:31-43); ResidLinear layers
+    (``layers.N.linear.*``) are returned like plain ones, pass resid=True to encoder_forward for them."""
+    return [(sd[w], sd[b]) for _, w, b in _linear_keys(sd)]
 
 
 def init_params(P_in: int, inf_dim: int, z_dim: int, H: int, L: int, Hq: int, Lq: int, C: int,
@@ -129,6 +144,8 @@ def flatten_params(dec, enc) -> List[torch.Tensor]:
     out = [dec["coord_w"], dec["coord_b"]]
     if dec["latent_w"] is not None:
         out.append(dec["latent_w"])
+    if dec.get("bilinear_w") is not None:
+        out.append(dec["bilinear_w"])
     for w, b in dec["hidden"]:
         out += [w, b]
     out += [dec["out_w"], dec["out_b"]]
@@ -141,6 +158,10 @@ def unflatten_like(dec, enc, flat: Sequence[torch.Tensor]):
     it = iter(flat)
     d = {"coord_w": next(it), "coord_b": next(it)}
     d["latent_w"] = next(it) if dec["latent_w"] is not None else None
+    if dec.get("bilinear_w") is not None:
+        d["bilinear_w"] = next(it)
+    if dec.get("resid"):
+        d["resid"] = True
     d["hidden"] = [(next(it), next(it)) for _ in dec["hidden"]]
     d["out_w"] = next(it)
     d["out_b"] = next(it)
@@ -162,13 +183,15 @@ def make_grid(n_rows: int, n_cols: int) -> torch.Tensor:
     return torch.from_numpy(np.stack([gx, gy], axis=1)).float()
 
 
-def encoder_forward(enc, y: torch.Tensor, activation: str = "tanh"):
+def encoder_forward(enc, y: torch.Tensor, activation: str = "tanh", resid: bool = False):
     """InferenceNetwork.forward (models.py:46-54): Linear+act per hidden layer, final Linear,
-    first half of the columns is z_mu, second half z_logstd."""
+    first half of the columns is z_mu, second half z_logstd.  resid: hidden layers after the first are
+    ResidLinear, act(linear(x) + x) (models.py:13-21,35-36)."""
     a = act_fn(activation)
     h = y
-    for w, b in enc[:-1]:
-        h = a(h @ w.t() + b)
+    for i, (w, b) in enumerate(enc[:-1]):
+        pre = h @ w.t() + b
+        h = a(pre + h) if (resid and i > 0) else a(pre)
     w, b = enc[-1]
     o = h @ w.t() + b
     half = o.shape[1] // 2
@@ -190,15 +213,22 @@ def transform_coords(grid: torch.Tensor, theta: Optional[torch.Tensor], dx: Opti
 
 def decoder_forward(dec, x: torch.Tensor, z: Optional[torch.Tensor], activation: str = "tanh",
                     softplus: bool = False) -> torch.Tensor:
-    """SpatialGenerator.forward (models.py:90-132), non-resid / non-bilinear / 2-D coords.
-    x (B,P,2), z (B,Z) -> (B,P,C) probabilities (the sigmoid is inside the module, :85)."""
+    """SpatialGenerator.forward (models.py:90-132).  x (B,P,2), z (B,Z) -> (B,P,C) probabilities (the sigmoid is
+    inside the module, :85).  Options follow the parameters present: 5 coordinate features when coord_w has 5
+    columns (expand_coords, :99-102: x, x^2, x0*x1), a bilinear term when ``bilinear_w`` is given (:114-121),
+    ResidLinear hidden layers when ``resid`` is set (:79-80)."""
     a = act_fn(activation)
+    if dec["coord_w"].shape[1] == 5:                                 # :99-102
+        x = torch.cat([x, x ** 2, (x[..., 0] * x[..., 1]).unsqueeze(-1)], dim=-1)
     h = x @ dec["coord_w"].t() + dec["coord_b"]                     # :104
     if dec["latent_w"] is not None and z is not None:
         h = h + (z @ dec["latent_w"].t())[:, None, :]                # :111-112,123
+        if dec.get("bilinear_w") is not None:                        # nn.Bilinear(x, z): sum_ij x_i W[n,i,j] z_j
+            h = h + torch.einsum("bpi,nij,bj->bpn", x, dec["bilinear_w"], z)
     h = a(h)                                                         # layers[0]
     for w, b in dec["hidden"]:
-        h = a(h @ w.t() + b)
+        pre = h @ w.t() + b
+        h = a(pre + h) if dec.get("resid") else a(pre)
     y = torch.sigmoid(h @ dec["out_w"].t() + dec["out_b"])           # :84-85
     if softplus:                                                     # :129-130
         y = torch.cat([F.softplus(y[..., :1]), y[..., 1:]], dim=-1)
@@ -234,7 +264,7 @@ def step_forward(cfg: StepConfig, dec, enc, grid: torch.Tensor, y: torch.Tensor,
     """
     B = y.shape[0]
     yin = (y if y_enc is None else y_enc).reshape(B, -1)
-    z_mu, z_logstd = encoder_forward(enc, yin, cfg.activation)      # train_mnist.py:32
+    z_mu, z_logstd = encoder_forward(enc, yin, cfg.activation, cfg.resid)      # train_mnist.py:32
     z_std = torch.exp(z_logstd)                                      # :33
     lat = z_std * eps + z_mu                                         # :39
 

@@ -145,6 +145,31 @@ def particles_case(name, fit_noise=False, use_ctf=False, use_mask=False, augment
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(p, q, extra))
 
 
+def particles_option_case(name, seed, **opts):
+    """--resid / --expand-coords / --bilinear / --softplus decoders and --resid encoders (train_particles.py:289-293,
+    437-444): options the B200 kernels do not implement yet; the fixtures pin the oracle for when they do."""
+    n, B, Z = 6, 4, 2
+    P, I = n * n, Z + 3
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = ref_models.SpatialGenerator(Z, 16, n_out=1, num_layers=3, activation=nn.Tanh,
+                                        softplus=opts.get("softplus", False), resid=opts.get("resid", False),
+                                        expand_coords=opts.get("expand_coords", False),
+                                        bilinear=opts.get("bilinear", False))
+        q = ref_models.InferenceNetwork(P, I, 12, num_layers=3, activation=nn.Tanh, resid=opts.get("resid", False))
+    g = torch.Generator().manual_seed(600 + seed)
+    y = torch.randn(B, P, generator=g)
+    eps = torch.randn(B, I, generator=g)
+    x = grid_of(n, n)
+    with inject_eps(eps):
+        elbo, logp, kl = train_particles.eval_minibatch(x, y, None, None, p, q, rotate=True, translate=True,
+                                                       dx_scale=0.1, theta_prior=np.pi)
+    (-elbo).backward()
+    extra = dict(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, n=n, z_scale=1.0, theta_prior=np.pi, dx_scale=0.1,
+                 **{"opt_" + k: int(v) for k, v in opts.items()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(p, q, extra))
+
+
 def galaxy_case(name, n=4, B=3, Z=4, L=3, seed=3, z_scale=1.0):
     P = n * n
     I = Z + 3
@@ -231,6 +256,11 @@ if __name__ == "__main__":
     particles_case("particles_mask", use_mask=True, seed=23)
     particles_case("particles_augment", augment=True, seed=24)
     particles_case("particles_zscale0", z_scale=0.0, seed=25)
+    particles_option_case("particles_opt_resid", 31, resid=True)
+    particles_option_case("particles_opt_expand", 32, expand_coords=True)
+    particles_option_case("particles_opt_bilinear", 33, bilinear=True)
+    particles_option_case("particles_opt_softplus", 34, softplus=True)
+    particles_option_case("particles_opt_all", 35, resid=True, expand_coords=True, bilinear=True, softplus=True)
     galaxy_case("galaxy_rgb")
     trajectory_case("mnist_adam10")
     decoder_case("decoder_module")

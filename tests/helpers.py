@@ -33,6 +33,15 @@ def golden_grads(d, dtype=torch.float32):
     return O.flatten_params(dec, enc)
 
 
+def option_cfg(d, family="particles"):
+    """StepConfig of a particles_opt_* fixture (softplus / resid flags; expand_coords and bilinear follow from
+    the parameter shapes)."""
+    cfg = cfg_of(d, family)
+    cfg.softplus = bool(int(d.get("opt_softplus", 0)))
+    cfg.resid = bool(int(d.get("opt_resid", 0)))
+    return cfg
+
+
 def cfg_of(d, family):
     return O.StepConfig(
         family=family,

@@ -468,6 +468,23 @@ def test_softplus_output_channel_matches_oracle(precision):
 
 
 @_unvalidated
+@pytest.mark.parametrize("precision", ["parity", "fast"])
+def test_softplus_golden_fixture(precision):
+    """--softplus against the reference-generated fixture (3-layer decoder and encoder)."""
+    from tests.helpers import option_cfg
+    d = load_case("particles_opt_softplus")
+    dec, enc = oracle_params(d)
+    cfg = option_cfg(d)
+    grid, y, eps, kw = _golden_inputs(d)
+    stats, _, grads = _run_cuda(cfg, dec, enc, grid, y, eps, precision)
+    tol = 2e-5 if precision == "parity" else 1e-3
+    assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= tol * abs(float(d["elbo"])) + 1e-5
+    if precision == "parity":
+        for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
+            np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=5e-4, atol=5e-6, err_msg=f"grad {i}")
+
+
+@_unvalidated
 def test_activation_variants_match_oracle():
     """ReLU and sigmoid hidden activations (train_galaxy.py:426-434) in both precisions."""
     for act in ("relu", "sigmoid"):
