@@ -306,6 +306,31 @@ def add_b200_flags(parser, hyphen=False):
     parser.add_argument(f'--synthetic{sep}size', type=int, default=0, help='image side for --synthetic')
 
 
+def normalize_particles(images):
+    """Per-particle zero mean / unit std over the pixels (reference train_particles.py:339-347)."""
+    n, m = images.shape[1:]
+    flat = images.reshape(-1, n * m)
+    mu, std = flat.mean(1), flat.std(1)
+    return (images - mu[:, np.newaxis, np.newaxis]) / std[:, np.newaxis, np.newaxis]
+
+
+def circular_mask(n, m):
+    """Boolean (n*m,) mask of the pixels closer than min(n,m)/2 to (n/2, m/2) (reference train_particles.py:387-396)."""
+    yy, xx = np.ogrid[:n, :m]
+    dist = np.sqrt((n / 2 - yy) ** 2 + (m / 2 - xx) ** 2)
+    return (torch.from_numpy(dist) < min(n, m) / 2).view(-1)
+
+
+def load_particle_stack(path):
+    """.mrc/.mrcs through spatial_vae.mrc, .npy through numpy (reference train_particles.py:248-255)."""
+    if path.endswith('mrc') or path.endswith('mrcs'):
+        from . import mrc
+        with open(path, 'rb') as f:
+            images, _, _ = mrc.parse(f.read())
+        return images
+    return np.load(path)
+
+
 def write_results(output_dir, train_lines, val_lines):
     with open(os.path.join(output_dir, 'train.txt'), 'w') as f:
         print('\n'.join(train_lines), file=f)

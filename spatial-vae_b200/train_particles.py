@@ -18,7 +18,6 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import spatial_vae.models as models            # noqa: E402
 import spatial_vae.functional as SF            # noqa: E402
 import spatial_vae.ctf as C                    # noqa: E402
-import spatial_vae.mrc as mrc                  # noqa: E402
 from spatial_vae import driver as D            # noqa: E402
 from spatial_vae.trainer import Trainer        # noqa: E402
 
@@ -68,12 +67,7 @@ def parse(argv=None):
     return p.parse_args(argv)
 
 
-def load_images(path):
-    if path.endswith('mrc') or path.endswith('mrcs'):
-        with open(path, 'rb') as f:
-            images, _, _ = mrc.parse(f.read())
-        return images
-    return np.load(path)
+load_images = D.load_particle_stack
 
 
 def main(argv=None):
@@ -105,10 +99,7 @@ def main(argv=None):
     n, m = images_train.shape[1:]
     if args.normalize:
         print('# normalizing particles', file=sys.stderr)
-        for arr in (images_train, images_test):
-            flat = arr.reshape(-1, n * m)
-            arr -= flat.mean(1)[:, None, None]
-            arr /= flat.std(1)[:, None, None]
+        images_train, images_test = D.normalize_particles(images_train), D.normalize_particles(images_test)
 
     # CTF kernels are odd-sized: 40x40 images get 39x39 kernels (reference train_particles.py:353-358)
     kn, km = (n - 1 if n % 2 == 0 else n), (m - 1 if m % 2 == 0 else m)
@@ -126,9 +117,7 @@ def main(argv=None):
     mask = None
     if args.mask:   # circular mask (reference train_particles.py:387-396)
         print('# masking particles', file=sys.stderr)
-        yy, xx = np.ogrid[:n, :m]
-        dist = np.sqrt((n / 2 - yy) ** 2 + (m / 2 - xx) ** 2)
-        mask = (torch.from_numpy(dist) < min(n, m) / 2).view(-1).to(device)
+        mask = D.circular_mask(n, m).to(device)
         print('# masking to size:', int(mask.sum()), file=sys.stderr)
 
     print('# training with z-dim:', args.z_dim, file=sys.stderr)

@@ -103,3 +103,33 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_particle_preprocessing_matches_reference_recipes(tmp_path):
+    """normalize / mask / stack loading of the particle CLI against the reference's inline code
+    (train_particles.py:248-255, 339-347, 387-396), restated here."""
+    import torch
+    import spatial_vae.mrc as M
+    from spatial_vae import driver as D
+    rng = np.random.default_rng(2)
+    imgs = (rng.standard_normal((5, 8, 6)) * 3 + 10).astype(np.float32)
+    n, m = imgs.shape[1:]
+    mu = imgs.reshape(-1, n * m).mean(1)
+    std = imgs.reshape(-1, n * m).std(1)
+    ref = (imgs - mu[:, np.newaxis, np.newaxis]) / std[:, np.newaxis, np.newaxis]
+    got = D.normalize_particles(imgs)
+    assert got.dtype == ref.dtype and np.array_equal(got, ref)
+    ints = (imgs * 10).astype(np.int16)                    # MRC mode 1 stacks are integers
+    assert np.allclose(D.normalize_particles(ints).reshape(5, -1).std(1), 1.0)
+
+    radius = min(n, m) / 2
+    y_grid, x_grid = np.ogrid[:n, :m]
+    center = np.array([n / 2, m / 2])
+    dist = np.sqrt((center[0] - y_grid) ** 2 + (center[1] - x_grid) ** 2)
+    assert torch.equal(D.circular_mask(n, m), (torch.from_numpy(dist) < radius).view(-1))
+
+    np.save(tmp_path / "stack.npy", imgs)
+    assert np.array_equal(D.load_particle_stack(str(tmp_path / "stack.npy")), imgs)
+    with open(tmp_path / "stack.mrcs", "wb") as f:
+        M.write(f, imgs)
+    assert np.array_equal(D.load_particle_stack(str(tmp_path / "stack.mrcs")), imgs)
