@@ -84,17 +84,21 @@ typedef struct {
     float   dx_scale;        /* std of the translation prior                                   */
     float   z_scale;         /* multiplies z only (train_particles.py:99); mnist: 1            */
     float   grad_scale;      /* 1 / (global minibatch size): gradients are of -mean_b(elbo_b)  */
+    int32_t resid;           /* hidden layers of BOTH networks are ResidLinear, act(W h + b + h) (models.py:13-21,35-36,79-80) */
+    int32_t expand_coords;   /* first layer sees (x0, x1, x0^2, x1^2, x0*x1): coord_w is (H, 5) (models.py:65-67,99-102) */
+    int32_t bilinear;        /* h0 += Bilinear(features, z) (models.py:74-75,114-121); needs bilinear_w and Z > 0 */
 } SvaeConfig;
 
 /* SpatialGenerator parameters (models.py:69-87). Gradient structs use the same layout. */
 typedef struct {
-    float* coord_w;                       /* (H, 2)  coord_linear.weight                       */
+    float* coord_w;                       /* (H, 2)  coord_linear.weight; (H, 5) with expand_coords */
     float* coord_b;                       /* (H)     coord_linear.bias                         */
     float* latent_w;                      /* (H, Z)  latent_linear.weight, NULL when Z == 0    */
     float* hidden_w[SVAE_MAX_LAYERS];     /* (H, H)  layers.{1,3,..}.weight, L-1 entries       */
     float* hidden_b[SVAE_MAX_LAYERS];     /* (H)                                               */
     float* out_w;                         /* (C, H)  last Linear                               */
     float* out_b;                         /* (C)                                               */
+    float* bilinear_w;                    /* (H, F, Z) bilinear.weight, F = 2 or 5; NULL unless cfg.bilinear */
 } SvaeDecoderParams;
 
 /* InferenceNetwork parameters (models.py:31-41): Lq hidden Linears then the head (2I, Hq). */
@@ -133,7 +137,9 @@ int  svae_device_sm_count(void);
 int  svae_workspace_bytes(const SvaeShape* shape, const SvaeConfig* cfg, size_t* bytes);
 
 /* InferenceNetwork.forward: x (B, P*Cin) -> out (B, 2I) = [z_mu | z_logstd].
- * acts: scratch (Lq, B, Hq) receiving the hidden activations (needed by the backward). */
+ * acts: scratch (Lq, B, Hq) receiving the hidden activations (needed by the backward).
+ * activation: SVAE_ACT_*, OR-ed with SVAE_ENC_RESID when hidden layers 1..Lq-1 are ResidLinear (models.py:35-36). */
+#define SVAE_ENC_RESID 0x100
 int  svae_encoder_forward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params,
                           const float* x, float* out, float* acts, void* stream);
 /* Backward of the above: g_out (B, 2I) is overwritten as scratch; grads are ACCUMULATED (+=)

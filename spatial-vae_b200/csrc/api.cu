@@ -38,6 +38,13 @@ struct Plan {
     // encoder on tensor cores (FAST): leading dimension of the fp32 activations and the bf16 split buffers
     int enc_ld = 0;
     size_t xs_k, gs_r, as_r, ws_k[SVAE_MAX_LAYERS], ws_r[SVAE_MAX_LAYERS];
+    // decoder options (models.py:65-67,74-75): F coordinate features, K1 per-image moment rows in S,
+    // opt = first layer runs through option_kernels.cu; weff (B, H*F) per-image coordinate weights (bilinear),
+    // dlat (B,3) = (d theta, d t0, d t1)
+    int F = 2, K1 = 3;
+    bool opt = false;
+    size_t weff = 0, dlat = 0;
+    long w_img_stride = 0;
 };
 
 static size_t take(size_t& cur, size_t bytes) {
@@ -68,13 +75,24 @@ static int validate(const SvaeShape& s, const SvaeConfig& c) {
         SVAE_REQUIRE(c.likelihood == SVAE_LIK_BERNOULLI, SVAE_EINVAL, "unknown likelihood %d", c.likelihood);
         SVAE_REQUIRE(s.k_ctf == 0, SVAE_EINVAL, "CTF only applies to the Gaussian likelihood");
     }
+    SVAE_REQUIRE(!c.bilinear || s.Z > 0, SVAE_EINVAL, "bilinear needs a latent (models.py:73-75)");
     return SVAE_OK;
 }
 
+// ResidLinear networks (models.py:13-21) run the fp32 kernels whatever cfg.precision says: the skip connection rides
+// in the FFMA GEMM epilogue exactly.  Folding it into the bf16 operand (W + I) rounds the diagonal to 2^-8 and was
+// measured (CPU emulation, H = 500, L = 3) at 3e-3..9e-3 relative per-image ELBO error, outside the 1e-3 gate; a
+// tcgen05 epilogue that adds the layer input tile is the next step for this option.
+static bool use_fast(const SvaeConfig& c) { return c.precision == SVAE_PRECISION_FAST && !c.resid; }
+
 static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
-    const bool fast = (c.precision == SVAE_PRECISION_FAST);
+    const bool fast = use_fast(c);
     p.Hp = fast ? (int)round_up(s.H, 64) : (int)round_up(s.H, 2);
     p.esize = fast ? 2 : 4;
+    p.F = c.expand_coords ? 5 : 2;
+    p.opt = c.expand_coords || c.bilinear;
+    p.K1 = p.opt ? p.F + 1 : 3;
+    p.w_img_stride = c.bilinear ? (long)s.H * p.F : 0;
     int chunk = c.chunk_images;
     if (chunk <= 0) {
         // bound the activation workspace (L act + 2 delta matrices) to ~6 GiB per pass
@@ -108,7 +126,9 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.img = take(cur, B * 4 * 4);
     p.zs = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
     p.hz = take(cur, B * p.Hp * 4);
-    p.S = take(cur, B * 3 * p.Hp * 4);
+    p.S = take(cur, B * p.K1 * p.Hp * 4);
+    p.weff = take(cur, c.bilinear ? B * (size_t)s.H * p.F * 4 : 0);
+    p.dlat = take(cur, B * 3 * 4);
     p.dz = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
     p.g_zo = take(cur, B * 2 * I * 4);
     p.o = take(cur, rows * s.C * 4);
@@ -141,8 +161,9 @@ static int encoder_head_forward(const SvaeShape& s, const SvaeEncoderParams& q, 
     return sgemm(a, st);
 }
 
+// resid: hidden layers 1..Lq-1 are ResidLinear, act(W h + b + h) (models.py:13-21,35-36)
 static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x, float* out,
-                                float* acts, cudaStream_t st) {
+                                float* acts, cudaStream_t st, bool resid = false) {
     const int n_in = s.P * s.Cin;
     const float* cur = x;
     int k = n_in;
@@ -154,6 +175,7 @@ static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderPa
         a.C = dst; a.ldc = s.Hq;
         a.M = s.B; a.N = s.Hq; a.K = k;
         a.bias = q.b[l]; a.act = act;
+        if (resid && l > 0) { a.add = cur; a.ld_add = k; }
         SVAE_TRY(sgemm(a, st));
         cur = dst; k = s.Hq;
     }
@@ -240,7 +262,7 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
 
 static int encoder_backward_impl(const SvaeShape& s, int act, const SvaeEncoderParams& q, const float* x,
                                  const float* acts, const float* g_out, SvaeEncoderParams& gq, float* g_x,
-                                 float* scratch, cudaStream_t st) {
+                                 float* scratch, cudaStream_t st, bool resid = false) {
     const int n_in = s.P * s.Cin;
     const size_t wide = (size_t)(s.Hq > 2 * s.I ? s.Hq : 2 * s.I);
     float* buf[2] = {scratch, scratch + (size_t)s.B * wide};
@@ -268,6 +290,7 @@ static int encoder_backward_impl(const SvaeShape& s, int act, const SvaeEncoderP
         d.C = dst; d.ldc = k_in;
         d.M = s.B; d.N = k_in; d.K = gn;
         if (l > 0) { d.dsrc = a_in; d.ld_dsrc = k_in; d.dact = act; }
+        if (resid && l > 0 && l < s.Lq) { d.add = g; d.ld_add = gn; }      // skip connection of ResidLinear l
         SVAE_TRY(sgemm(d, st));
         g = dst; gn = k_in;
     }
@@ -286,6 +309,8 @@ struct DecoderCtx {
     T* delta(int i) const { return reinterpret_cast<T*>(ws + p->delta + p->delta_stride * i); }
     float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
     __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
+    // first-layer coordinate weights of image 0: W_eff (B, H*F) with bilinear, else coord_linear.weight
+    const float* l0_w(const SvaeDecoderParams& dp) const { return c->bilinear ? f(p->weff) : dp.coord_w; }
 };
 
 // fuse_out: also accumulate the output-layer logits o (rows, C) (pre-filled with out_b) in the epilogue
@@ -300,6 +325,7 @@ int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& d
     a.C = d.act(l); a.ldc = Hp;
     a.M = rows; a.N = H; a.K = H;
     a.bias = dp.hidden_b[l - 1]; a.act = d.c->activation;
+    if (d.c->resid) { a.add = d.act(l - 1); a.ld_add = Hp; }     // ResidLinear: act(W h + b + h)
     return sgemm(a, d.st);
 }
 template <>
@@ -339,6 +365,7 @@ int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& 
     x.C = delta_prev; x.ldc = Hp;
     x.M = rows; x.N = H; x.K = H;
     x.dsrc = d.act(l - 1); x.ld_dsrc = Hp; x.dact = d.c->activation;
+    if (d.c->resid) { x.add = delta; x.ld_add = Hp; }            // gradient through the skip connection
     return sgemm(x, d.st);
 }
 template <>
@@ -365,8 +392,12 @@ static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams
     if (std::is_same<T, float>::value && Hp != s.H) {
         SVAE_CUDA(cudaMemsetAsync(d.ws + d.p->acts, 0, d.p->act_stride * s.L + d.p->delta_stride * 2, d.st));
     }
-    SVAE_TRY(layer0_forward<T>(s, d.c->activation, b0, nb, dp.coord_w, d.f(d.p->hz), grid, d.f(d.p->img), x_explicit,
-                               s.H, Hp, d.act(0), d.st));
+    if (d.p->opt)
+        SVAE_TRY(layer0_opt_forward<T>(d.p->F, s.P, d.c->activation, b0, nb, d.l0_w(dp), d.p->w_img_stride,
+                                       d.f(d.p->hz), grid, d.f(d.p->img), x_explicit, s.H, Hp, d.act(0), d.st));
+    else
+        SVAE_TRY(layer0_forward<T>(s, d.c->activation, b0, nb, dp.coord_w, d.f(d.p->hz), grid, d.f(d.p->img),
+                                   x_explicit, s.H, Hp, d.act(0), d.st));
     // FAST precision: the output-layer dot product rides in the epilogue of the last hidden GEMM
     const bool fuse_out = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3;
     for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows, fuse_out && l == s.L - 1));
@@ -390,7 +421,7 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     // SIMT reduction in the epilogue costs more than the HBM pass it removes -- so it is off by default.
     static const bool want_red = (getenv("SVAE_FUSE_RED") != nullptr && getenv("SVAE_FUSE_RED")[0] == '1');
     const bool fuse_red = want_red && !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr &&
-                          g_x == nullptr && (long)s.B < 32000;
+                          g_x == nullptr && (long)s.B < 32000 && !d.p->opt;
     bool reduced = false;
     for (int l = s.L - 1; l >= 1; --l) {
         RedSpec red;
@@ -398,6 +429,15 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
         SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1), red));
         cur ^= 1;
         if (l - 1 >= 1) SVAE_TRY(col_sum<T>(d.delta(cur), rows, s.H, Hp, g.hidden_b[l - 2], d.st));
+    }
+    if (d.p->opt) {
+        SVAE_TRY(image_feat_reduce<T>(d.p->F, d.delta(cur), b0, nb, s.P, Hp, grid, d.f(d.p->img), x_explicit,
+                                      d.f(d.p->S), d.st));
+        if (g_x)
+            SVAE_TRY(coord_row_grad_opt<T>(d.p->F, d.delta(cur), rows, s.P, s.H, Hp,
+                                           d.l0_w(dp) + (size_t)b0 * d.p->w_img_stride, d.p->w_img_stride,
+                                           x_explicit + (size_t)b0 * s.P * 2, g_x + (size_t)b0 * s.P * 2, d.st));
+        return SVAE_OK;
     }
     if (!reduced) SVAE_TRY(image_col_reduce<T>(d.delta(cur), b0, nb, s.P, Hp, grid, x_explicit, d.f(d.p->S), d.st));
     if (g_x) SVAE_TRY(coord_row_grad<T>(d.delta(cur), rows, s.H, Hp, dp.coord_w, g_x + (size_t)b0 * s.P * 2, d.st));
@@ -427,6 +467,73 @@ static int latent_projection(const SvaeShape& s, const Plan& p, const SvaeDecode
         return sgemm(a, st);
     }
     return fill_rows(hz, dp.coord_b, s.B, s.H, p.Hp, st);
+}
+
+// bilinear (models.py:114-121): per-image coordinate weights W_eff (B, H*F) = zs Wb^T + Wc, Wb viewed as (H*F, Z)
+static int bilinear_weights(const SvaeShape& s, const Plan& p, const SvaeDecoderParams& dp, const float* zs,
+                            float* weff, cudaStream_t st) {
+    if (s.B == 0) return SVAE_OK;
+    SgemmArgs a{};
+    a.A = zs; a.sAm = s.Z; a.sAk = 1;
+    a.B = dp.bilinear_w; a.sBk = 1; a.sBn = s.Z;
+    a.C = weff; a.ldc = (long)s.H * p.F;
+    a.M = s.B; a.N = s.H * p.F; a.K = s.Z;
+    a.bias = dp.coord_w;
+    return sgemm(a, st);
+}
+
+// option path of first_layer_param_grads: T (B, F+1, Hp) are the feature moments of delta0 (first_layer.cuh)
+static int first_layer_param_grads_opt(const SvaeShape& s, const SvaeConfig& c, const Plan& p,
+                                       const SvaeDecoderParams& dp, SvaeDecoderParams& g, const float* T,
+                                       const float* zs, float z_scale, float* dz, cudaStream_t st) {
+    if (s.B == 0) return SVAE_OK;
+    const int F = p.F;
+    const long ldT = (long)(F + 1) * p.Hp;
+    SVAE_TRY(coord_param_grad_opt(F, T, s.B, s.H, p.Hp, g.coord_w, g.coord_b, st));
+    if (s.Z == 0 || dp.latent_w == nullptr) return SVAE_OK;
+    const int split_b = s.B >= 512 ? 8 : (s.B >= 128 ? 2 : 1);
+    // dWz (H,Z) += T_0^T zs
+    SgemmArgs w{};
+    w.A = T; w.sAm = 1; w.sAk = ldT;
+    w.B = zs; w.sBk = s.Z; w.sBn = 1;
+    w.C = g.latent_w; w.ldc = s.Z;
+    w.M = s.H; w.N = s.Z; w.K = s.B;
+    w.accumulate = 1; w.split_k = split_b;
+    SVAE_TRY(sgemm(w, st));
+    if (dz) {
+        // dz (B,Z) = z_scale * T_0 Wz
+        SVAE_CUDA(cudaMemsetAsync(dz, 0, (size_t)s.B * s.Z * sizeof(float), st));
+        SgemmArgs x{};
+        x.A = T; x.sAm = ldT; x.sAk = 1;
+        x.B = dp.latent_w; x.sBk = s.Z; x.sBn = 1;
+        x.C = dz; x.ldc = s.Z;
+        x.M = s.B; x.N = s.Z; x.K = s.H;
+        x.alpha = z_scale; x.accumulate = 1;
+        SVAE_TRY(sgemm(x, st));
+    }
+    if (!c.bilinear) return SVAE_OK;
+    for (int i = 0; i < F; ++i) {
+        const float* Ti = T + (size_t)(1 + i) * p.Hp;              // dW_eff[b][n,i] = T[b][1+i][n]
+        // dWb[n,i,j] += sum_b T[b][1+i][n] zs[b,j]
+        SgemmArgs wb{};
+        wb.A = Ti; wb.sAm = 1; wb.sAk = ldT;
+        wb.B = zs; wb.sBk = s.Z; wb.sBn = 1;
+        wb.C = g.bilinear_w + (size_t)i * s.Z; wb.ldc = (long)F * s.Z;
+        wb.M = s.H; wb.N = s.Z; wb.K = s.B;
+        wb.accumulate = 1; wb.split_k = split_b;
+        SVAE_TRY(sgemm(wb, st));
+        if (dz) {
+            // dz[b,j] += z_scale * sum_n T[b][1+i][n] Wb[n,i,j]
+            SgemmArgs xb{};
+            xb.A = Ti; xb.sAm = ldT; xb.sAk = 1;
+            xb.B = dp.bilinear_w + (size_t)i * s.Z; xb.sBk = (long)F * s.Z; xb.sBn = 1;
+            xb.C = dz; xb.ldc = s.Z;
+            xb.M = s.B; xb.N = s.Z; xb.K = s.H;
+            xb.alpha = z_scale; xb.accumulate = 1;
+            SVAE_TRY(sgemm(xb, st));
+        }
+    }
+    return SVAE_OK;
 }
 
 // gradients that flow through S: coord layer, latent_linear, and dz (B,Z)
@@ -481,12 +588,13 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     constexpr bool kFast = !std::is_same<T, float>::value;
     EncTc enc_tc{&s, &p, ws, st};
     if (kFast) SVAE_TRY(encoder_forward_tc(enc_tc, c.activation, qp, x_enc, zo));
-    else SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st));
+    else SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st, c.resid != 0));
     float* lat = out.latent ? out.latent : d.f(p.lat);
     SVAE_TRY(latent_forward(s, c, zo, in.eps, in.theta_offset, lat, d.f(p.img), d.f(p.zs), out.stats, st));
     SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
+    if (c.bilinear) SVAE_TRY(bilinear_weights(s, p, dp, d.f(p.zs), d.f(p.weff), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
-    if (train && kFast) SVAE_CUDA(cudaMemsetAsync(ws + p.S, 0, (size_t)s.B * 3 * p.Hp * sizeof(float), st));
+    if (train && kFast) SVAE_CUDA(cudaMemsetAsync(ws + p.S, 0, (size_t)s.B * p.K1 * p.Hp * sizeof(float), st));
     for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
         const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
         SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, in.grid, nullptr, out.y_hat));
@@ -496,14 +604,23 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
     SVAE_LAUNCH_CHECK();
     if (train) {
-        SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
-                                         s.Z > 0 ? d.f(p.dz) : nullptr, st));
-        SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
-                                 in.eps, d.f(p.g_zo), st));
+        if (p.opt) {
+            SVAE_TRY(first_layer_param_grads_opt(s, c, p, dp, *gd, d.f(p.S), d.f(p.zs), c.z_scale,
+                                                 s.Z > 0 ? d.f(p.dz) : nullptr, st));
+            SVAE_TRY(latent_coord_grad(p.F, s.B, s.H, p.Hp, d.l0_w(dp), p.w_img_stride, d.f(p.S), d.f(p.img),
+                                       d.f(p.dlat), st));
+            SVAE_TRY(latent_backward(s, c, nullptr, p.Hp, d.f(p.img), nullptr, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
+                                     in.eps, d.f(p.g_zo), st, d.f(p.dlat)));
+        } else {
+            SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
+                                             s.Z > 0 ? d.f(p.dz) : nullptr, st));
+            SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
+                                     in.eps, d.f(p.g_zo), st));
+        }
         if (gq) {
             if (kFast) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));
             else SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
-                                                d.f(p.enc_scratch), st));
+                                                d.f(p.enc_scratch), st, c.resid != 0));
         }
     }
     return SVAE_OK;
@@ -541,6 +658,7 @@ static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, 
         SVAE_LAUNCH_CHECK();
     }
     SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
+    if (c.bilinear) SVAE_TRY(bilinear_weights(s, p, dp, d.f(p.zs), d.f(p.weff), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
     for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
         const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
@@ -554,7 +672,8 @@ static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, 
         }
     }
     if (gd) {
-        SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), nullptr, d.f(p.zs), 1.f, 1, g_z, st));
+        if (p.opt) SVAE_TRY(first_layer_param_grads_opt(s, c, p, dp, *gd, d.f(p.S), d.f(p.zs), 1.f, g_z, st));
+        else SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), nullptr, d.f(p.zs), 1.f, 1, g_z, st));
     }
     return SVAE_OK;
 }
@@ -598,7 +717,8 @@ int svae_encoder_forward(const SvaeShape* shape, int activation, const SvaeEncod
     SVAE_REQUIRE(shape && params && x && out && acts, SVAE_EINVAL, "null argument");
     SVAE_REQUIRE(shape->Lq >= 1 && shape->Lq <= SVAE_MAX_LAYERS, SVAE_EINVAL, "bad encoder depth %d", shape->Lq);
     if (shape->B == 0) return SVAE_OK;
-    return encoder_forward_impl(*shape, activation, *params, x, out, acts, (cudaStream_t)stream);
+    return encoder_forward_impl(*shape, activation & 0xff, *params, x, out, acts, (cudaStream_t)stream,
+                                (activation & SVAE_ENC_RESID) != 0);
 }
 
 int svae_encoder_backward(const SvaeShape* shape, int activation, const SvaeEncoderParams* params, const float* x,
@@ -606,14 +726,15 @@ int svae_encoder_backward(const SvaeShape* shape, int activation, const SvaeEnco
                           void* stream) {
     SVAE_REQUIRE(shape && params && x && acts && g_out && grads && scratch, SVAE_EINVAL, "null argument");
     if (shape->B == 0) return SVAE_OK;
-    return encoder_backward_impl(*shape, activation, *params, x, acts, g_out, *grads, g_x, scratch,
-                                 (cudaStream_t)stream);
+    return encoder_backward_impl(*shape, activation & 0xff, *params, x, acts, g_out, *grads, g_x, scratch,
+                                 (cudaStream_t)stream, (activation & SVAE_ENC_RESID) != 0);
 }
 
 static int decoder_shape_check(const SvaeShape& s, const SvaeConfig& c) {
     SVAE_REQUIRE(s.B >= 0 && s.P > 0 && s.H > 0 && s.L >= 1 && s.L <= SVAE_MAX_LAYERS && s.C >= 1 && s.C <= 4,
                  SVAE_EINVAL, "bad decoder shape");
     SVAE_REQUIRE(c.activation >= 0 && c.activation <= 3, SVAE_EINVAL, "unknown activation %d", c.activation);
+    SVAE_REQUIRE(!c.bilinear || s.Z > 0, SVAE_EINVAL, "bilinear needs a latent (models.py:73-75)");
     return SVAE_OK;
 }
 
@@ -622,10 +743,11 @@ int svae_decoder_forward(const SvaeShape* shape, const SvaeConfig* cfg, const Sv
                          void* stream) {
     SVAE_REQUIRE(shape && cfg && params && x && y_hat && workspace, SVAE_EINVAL, "null argument");
     SVAE_TRY(decoder_shape_check(*shape, *cfg));
+    SVAE_REQUIRE(!cfg->bilinear || (params->bilinear_w && z), SVAE_EINVAL, "cfg.bilinear needs bilinear_w and z");
     Plan p;
     SVAE_TRY(make_plan(*shape, *cfg, p));
     SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
-    if (cfg->precision == SVAE_PRECISION_FAST)
+    if (use_fast(*cfg))
         return decoder_impl<__nv_bfloat16>(*shape, *cfg, p, *params, x, z, y_hat, nullptr, nullptr, nullptr, nullptr,
                                            (char*)workspace, (cudaStream_t)stream);
     return decoder_impl<float>(*shape, *cfg, p, *params, x, z, y_hat, nullptr, nullptr, nullptr, nullptr,
@@ -637,10 +759,12 @@ int svae_decoder_backward(const SvaeShape* shape, const SvaeConfig* cfg, const S
                           float* g_z, void* workspace, size_t workspace_bytes, void* stream) {
     SVAE_REQUIRE(shape && cfg && params && x && g_y && grads && workspace, SVAE_EINVAL, "null argument");
     SVAE_TRY(decoder_shape_check(*shape, *cfg));
+    SVAE_REQUIRE(!cfg->bilinear || (params->bilinear_w && grads->bilinear_w && z), SVAE_EINVAL,
+                 "cfg.bilinear needs bilinear_w (parameters and gradients) and z");
     Plan p;
     SVAE_TRY(make_plan(*shape, *cfg, p));
     SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
-    if (cfg->precision == SVAE_PRECISION_FAST)
+    if (use_fast(*cfg))
         return decoder_impl<__nv_bfloat16>(*shape, *cfg, p, *params, x, z, nullptr, g_y, grads, g_x, g_z,
                                            (char*)workspace, (cudaStream_t)stream);
     return decoder_impl<float>(*shape, *cfg, p, *params, x, z, nullptr, g_y, grads, g_x, g_z, (char*)workspace,
@@ -658,11 +782,13 @@ int svae_step(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderPa
     SVAE_REQUIRE((shape->k_ctf > 0) == (in->ctf != nullptr), SVAE_EINVAL, "k_ctf and the ctf pointer disagree");
     SVAE_REQUIRE((dec_grads == nullptr) == (enc_grads == nullptr), SVAE_EINVAL,
                  "pass both gradient structs or neither");
+    SVAE_REQUIRE(!cfg->bilinear || (dec->bilinear_w && (dec_grads == nullptr || dec_grads->bilinear_w)), SVAE_EINVAL,
+                 "cfg.bilinear needs bilinear_w (parameters and gradients)");
     if (shape->B == 0) return SVAE_OK;
     Plan p;
     SVAE_TRY(make_plan(*shape, *cfg, p));
     SVAE_REQUIRE(workspace_bytes >= p.total, SVAE_ENOSPACE, "workspace %zu < %zu bytes", workspace_bytes, p.total);
-    if (cfg->precision == SVAE_PRECISION_FAST)
+    if (use_fast(*cfg))
         return step_impl<__nv_bfloat16>(*shape, *cfg, p, *dec, *enc, *in, *out, dec_grads, enc_grads,
                                         (char*)workspace, (cudaStream_t)stream);
     return step_impl<float>(*shape, *cfg, p, *dec, *enc, *in, *out, dec_grads, enc_grads, (char*)workspace,

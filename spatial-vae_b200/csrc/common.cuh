@@ -81,7 +81,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- fp32 SIMT GEMM (sgemm.cu) ---------------------------------------------------------------
 // C[m,n] (op)= alpha * sum_k A(m,k) * B(k,n)  with arbitrary element strides, then the epilogue
-//   v += bias[n];  v = act(v);  v *= act'(dsrc[m*ld_dsrc + n])
+//   v += bias[n];  v += add[m*ld_add + n];  v = act(v);  v *= act'(dsrc[m*ld_dsrc + n])
+// (add: the skip connection of a ResidLinear layer, models.py:13-21 -- the layer input in the forward,
+//  the incoming gradient in the backward)
 // accumulate = 1 adds into C with atomics (required when split_k > 1).
 struct SgemmArgs {
     const float* A; long sAm, sAk;
@@ -91,6 +93,7 @@ struct SgemmArgs {
     const float* bias = nullptr;
     int act = -1;
     const float* dsrc = nullptr; long ld_dsrc = 0; int dact = -1;
+    const float* add = nullptr; long ld_add = 0;
     int accumulate = 0;
     int split_k = 1;
     float alpha = 1.f;

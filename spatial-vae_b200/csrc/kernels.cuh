@@ -61,9 +61,30 @@ int coord_param_grad(const float* S, const float* img, int B, int H, int Hp, int
                      float* d_coord_b, cudaStream_t st);
 
 // Per-image latent gradient -> encoder head gradient g_zo (B,2I) (SURVEY 7.3 last line).
+// coord_pre: optional (B,3) = (d theta, d t0, d t1) already computed by latent_coord_grad (option path); when set,
+// S and coord_w are not read.
 int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
                     const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
-                    cudaStream_t st);
+                    cudaStream_t st, const float* coord_pre = nullptr);
+
+// ---- decoder options (option_kernels.cu): --expand-coords (F = 5 coordinate features) and --bilinear (per-image
+// coordinate weights w[b*w_img_stride + n*F + i]; stride 0 = coord_linear.weight shared by all images).
+// Tm (B, F+1, Hp) are the feature moments of delta0 (see first_layer.cuh).
+template <typename T>
+int layer0_opt_forward(int F, int P, int act, int b0, int nb, const float* w, long w_img_stride, const float* hz,
+                       const float* grid, const float* img, const float* x_explicit, int H, int Hp, T* h0,
+                       cudaStream_t st);
+template <typename T>
+int image_feat_reduce(int F, const T* delta0, int b0, int nb, int P, int Hp, const float* grid, const float* img,
+                      const float* x_explicit, float* Tm, cudaStream_t st);
+int coord_param_grad_opt(int F, const float* Tm, int B, int H, int Hp, float* d_coord_w, float* d_coord_b,
+                         cudaStream_t st);
+int latent_coord_grad(int F, int B, int H, int Hp, const float* w, long w_img_stride, const float* Tm,
+                      const float* img, float* out, cudaStream_t st);
+template <typename T>
+int coord_row_grad_opt(int F, const T* delta0, int rows, int P, int H, int Hp, const float* w, long w_img_stride,
+                       const float* x, float* g_x, cudaStream_t st);
+
 
 int adam_tick(int* t_dev, float* bias_corr_dev, float b1, float b2, cudaStream_t st);
 // bias_corr_dev: optional device pointer to {1 - b1^t, sqrt(1 - b2^t)}; when set it overrides t

@@ -1,0 +1,229 @@
+// First-layer kernels for the decoder options --expand-coords and --bilinear (reference models.py:65-67,74-75,
+// 99-102,114-121).
+// The arithmetic is first_layer.cuh (also compiled with g++ and checked against the oracle's autograd in
+// tests/test_first_layer_math.py); the kernels here add the thread indexing.
+//
+// Per-image coordinate weights: w[b * w_img_stride + n * F + i]; w_img_stride = 0 -> coord_linear.weight (H, F)
+// shared by all images, H*F -> W_eff (B, H*F) = Wc + z Wb^T (bilinear).
+// Feature moments of delta0: T (B, F+1, Hp):  T[b][0][n] = sum_p d,  T[b][1+i][n] = sum_p d * f_i(x'_bp).
+#include <type_traits>
+
+#include "first_layer.cuh"
+#include "kernels.cuh"
+
+namespace svae {
+
+namespace {
+__device__ __forceinline__ void ld2(const float* p, float& a, float& b) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    a = v.x; b = v.y;
+}
+__device__ __forceinline__ void ld2(const __nv_bfloat16* p, float& a, float& b) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+    a = __low2float(v); b = __high2float(v);
+}
+constexpr int OPT_ROWS = 64;
+}  // namespace
+
+// ---- forward --------------------------------------------------------------------------------------------------
+template <typename T, bool FAST, int F>
+__global__ void __launch_bounds__(256) layer0_opt_k(int P, int act, int b0, const float* __restrict__ w,
+                                                    long w_img_stride, const float* __restrict__ hz,
+                                                    const float* __restrict__ grid, const float* __restrict__ img,
+                                                    const float* __restrict__ xe, int H, int Hp,
+                                                    T* __restrict__ h0) {
+    __shared__ float sf[OPT_ROWS][F];
+    const int bl = blockIdx.y, b = b0 + bl;
+    const int p0 = blockIdx.x * OPT_ROWS;
+    const int nrows = min(OPT_ROWS, P - p0);
+    if (threadIdx.x < nrows) {
+        const int p = p0 + threadIdx.x;
+        float x0, x1;
+        if (xe) {
+            x0 = xe[((long)b * P + p) * 2 + 0];
+            x1 = xe[((long)b * P + p) * 2 + 1];
+        } else {
+            transform_coord(grid[p * 2], grid[p * 2 + 1], img[b * 4], img[b * 4 + 1], img[b * 4 + 2], img[b * 4 + 3],
+                            x0, x1);
+        }
+        float f[kMaxCoordFeatures];
+        coord_features<F>(x0, x1, f);
+#pragma unroll
+        for (int i = 0; i < F; ++i) sf[threadIdx.x][i] = f[i];
+    }
+    __syncthreads();
+    const float* wb = w + (long)b * w_img_stride;
+    T* out = h0 + ((long)bl * P + p0) * Hp;
+    for (int n = threadIdx.x; n < Hp; n += blockDim.x) {
+        float wn[F], hb = 0.f;
+#pragma unroll
+        for (int i = 0; i < F; ++i) wn[i] = (n < H) ? wb[(long)n * F + i] : 0.f;
+        if (n < H) hb = hz[(long)b * Hp + n];
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) {
+            float a = hb;
+#pragma unroll
+            for (int i = F - 1; i >= 0; --i) a = fmaf(wn[i], sf[r][i], a);
+            out[(long)r * Hp + n] = from_f32<T>(act_apply<FAST>(act, a));
+        }
+    }
+}
+
+template <typename T>
+int layer0_opt_forward(int F, int P, int act, int b0, int nb, const float* w, long w_img_stride, const float* hz,
+                       const float* grid, const float* img, const float* x_explicit, int H, int Hp, T* h0,
+                       cudaStream_t st) {
+    dim3 g(ceil_div(P, OPT_ROWS), nb);
+    constexpr bool FAST = !std::is_same<T, float>::value;
+    if (F == 5) layer0_opt_k<T, FAST, 5><<<g, 256, 0, st>>>(P, act, b0, w, w_img_stride, hz, grid, img, x_explicit, H, Hp, h0);
+    else        layer0_opt_k<T, FAST, 2><<<g, 256, 0, st>>>(P, act, b0, w, w_img_stride, hz, grid, img, x_explicit, H, Hp, h0);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int layer0_opt_forward<float>(int, int, int, int, int, const float*, long, const float*, const float*,
+                                       const float*, const float*, int, int, float*, cudaStream_t);
+template int layer0_opt_forward<__nv_bfloat16>(int, int, int, int, int, const float*, long, const float*, const float*,
+                                               const float*, const float*, int, int, __nv_bfloat16*, cudaStream_t);
+
+// ---- feature moments of delta0 ---------------------------------------------------------------------------------
+// block (image, column slab); thread = a pair of adjacent columns, walking the P rows of the image
+template <typename T, int F>
+__global__ void __launch_bounds__(256) image_feat_reduce_k(const T* __restrict__ d0, int b0, int P, int Hp,
+                                                           const float* __restrict__ grid,
+                                                           const float* __restrict__ img,
+                                                           const float* __restrict__ xe, float* __restrict__ Tm) {
+    const int bl = blockIdx.x, b = b0 + bl;
+    float cs = 1.f, sn = 0.f, t0 = 0.f, t1 = 0.f;       // explicit coordinates: identity transform
+    if (xe == nullptr) { cs = img[b * 4]; sn = img[b * 4 + 1]; t0 = img[b * 4 + 2]; t1 = img[b * 4 + 3]; }
+    const float* coords = xe ? xe + (long)b * P * 2 : grid;
+    const T* base = d0 + (long)bl * P * Hp;
+    float* Tb = Tm + (long)b * (F + 1) * Hp;
+    for (int pr = threadIdx.x + blockIdx.y * blockDim.x; pr < Hp / 2; pr += blockDim.x * gridDim.y) {
+        float a0[F + 1], a1[F + 1];
+#pragma unroll
+        for (int k = 0; k <= F; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+        for (int p = 0; p < P; ++p) {
+            float x, y;
+            ld2(base + (long)p * Hp + pr * 2, x, y);
+            const float2 c = __ldg(reinterpret_cast<const float2*>(coords) + p);
+            float x0, x1, f[kMaxCoordFeatures];
+            transform_coord(c.x, c.y, cs, sn, t0, t1, x0, x1);
+            coord_features<F>(x0, x1, f);
+            a0[0] += x; a1[0] += y;
+#pragma unroll
+            for (int i = 0; i < F; ++i) { a0[1 + i] = fmaf(f[i], x, a0[1 + i]); a1[1 + i] = fmaf(f[i], y, a1[1 + i]); }
+        }
+#pragma unroll
+        for (int k = 0; k <= F; ++k) { Tb[(long)k * Hp + pr * 2] = a0[k]; Tb[(long)k * Hp + pr * 2 + 1] = a1[k]; }
+    }
+}
+
+template <typename T>
+int image_feat_reduce(int F, const T* delta0, int b0, int nb, int P, int Hp, const float* grid, const float* img,
+                      const float* x_explicit, float* Tm, cudaStream_t st) {
+    dim3 g(nb, ceil_div(Hp / 2, 256));
+    if (F == 5) image_feat_reduce_k<T, 5><<<g, 256, 0, st>>>(delta0, b0, P, Hp, grid, img, x_explicit, Tm);
+    else        image_feat_reduce_k<T, 2><<<g, 256, 0, st>>>(delta0, b0, P, Hp, grid, img, x_explicit, Tm);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int image_feat_reduce<float>(int, const float*, int, int, int, int, const float*, const float*, const float*,
+                                      float*, cudaStream_t);
+template int image_feat_reduce<__nv_bfloat16>(int, const __nv_bfloat16*, int, int, int, int, const float*, const float*,
+                                              const float*, float*, cudaStream_t);
+
+// ---- d coord_linear from the moments: dWc[n,i] += sum_b T[b][1+i][n], dbc[n] += sum_b T[b][0][n] ---------------
+template <int F>
+__global__ void coord_param_grad_opt_k(const float* __restrict__ Tm, int B, int H, int Hp, float* __restrict__ dw,
+                                       float* __restrict__ db) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= H) return;
+    const int per = ceil_div(B, gridDim.y);
+    const int bs = blockIdx.y * per, be = min(B, bs + per);
+    float a[F + 1];
+#pragma unroll
+    for (int k = 0; k <= F; ++k) a[k] = 0.f;
+    for (int b = bs; b < be; ++b) {
+        const float* Tb = Tm + (long)b * (F + 1) * Hp;
+#pragma unroll
+        for (int k = 0; k <= F; ++k) a[k] += Tb[(long)k * Hp + n];
+    }
+    atomicAdd(db + n, a[0]);
+#pragma unroll
+    for (int i = 0; i < F; ++i) atomicAdd(dw + (long)n * F + i, a[1 + i]);
+}
+int coord_param_grad_opt(int F, const float* Tm, int B, int H, int Hp, float* d_coord_w, float* d_coord_b,
+                         cudaStream_t st) {
+    dim3 g(ceil_div(H, 128), min(ceil_div(B, 32), 64));
+    if (F == 5) coord_param_grad_opt_k<5><<<g, 128, 0, st>>>(Tm, B, H, Hp, d_coord_w, d_coord_b);
+    else        coord_param_grad_opt_k<2><<<g, 128, 0, st>>>(Tm, B, H, Hp, d_coord_w, d_coord_b);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ---- per image (d theta, d t0, d t1) from the moments; one warp per image ---------------------------------------
+template <int F>
+__global__ void __launch_bounds__(256) latent_coord_grad_k(int B, int H, int Hp, const float* __restrict__ w,
+                                                           long w_img_stride, const float* __restrict__ Tm,
+                                                           const float* __restrict__ img, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    const float* wb = w + (long)b * w_img_stride;
+    const float* Tb = Tm + (long)b * (F + 1) * Hp;
+    const float t0 = img[b * 4 + 2], t1 = img[b * 4 + 3];
+    float dth = 0.f, d0 = 0.f, d1 = 0.f;
+    for (int n = lane; n < H; n += 32) {
+        float a, c0, c1;
+        latent_coord_terms<F>(wb + (long)n * F, 1, Tb + n, Hp, t0, t1, a, c0, c1);
+        dth += a; d0 += c0; d1 += c1;
+    }
+    dth = warp_sum(dth); d0 = warp_sum(d0); d1 = warp_sum(d1);
+    if (lane == 0) { out[b * 3] = dth; out[b * 3 + 1] = d0; out[b * 3 + 2] = d1; }
+}
+int latent_coord_grad(int F, int B, int H, int Hp, const float* w, long w_img_stride, const float* Tm,
+                      const float* img, float* out, cudaStream_t st) {
+    if (B == 0) return SVAE_OK;
+    if (F == 5) latent_coord_grad_k<5><<<ceil_div(B, 8), 256, 0, st>>>(B, H, Hp, w, w_img_stride, Tm, img, out);
+    else        latent_coord_grad_k<2><<<ceil_div(B, 8), 256, 0, st>>>(B, H, Hp, w, w_img_stride, Tm, img, out);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+// ---- module path: gradient w.r.t. explicit coordinates; one warp per row -----------------------------------------
+template <typename T, int F>
+__global__ void __launch_bounds__(256) coord_row_grad_opt_k(const T* __restrict__ d0, int rows, int P, int H, int Hp,
+                                                            const float* __restrict__ w, long w_img_stride,
+                                                            const float* __restrict__ x, float* __restrict__ gx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long r = (long)blockIdx.x * 8 + warp; r < rows; r += (long)gridDim.x * 8) {
+        const float* wb = w + (r / P) * w_img_stride;
+        const float x0 = x[r * 2], x1 = x[r * 2 + 1];
+        float a0 = 0.f, a1 = 0.f;
+        for (int n = lane; n < H; n += 32) {
+            float j0, j1;
+            feature_jacobian<F>(wb + (long)n * F, 1, x0, x1, j0, j1);
+            const float d = to_f32(d0[r * Hp + n]);
+            a0 = fmaf(d, j0, a0);
+            a1 = fmaf(d, j1, a1);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1);
+        if (lane == 0) { gx[r * 2] = a0; gx[r * 2 + 1] = a1; }
+    }
+}
+// d0, x, gx and w all start at the first image of the chunk
+template <typename T>
+int coord_row_grad_opt(int F, const T* delta0, int rows, int P, int H, int Hp, const float* w, long w_img_stride,
+                       const float* x, float* g_x, cudaStream_t st) {
+    const int blocks = min(ceil_div(rows, 8), 148 * 8);
+    if (F == 5) coord_row_grad_opt_k<T, 5><<<blocks, 256, 0, st>>>(delta0, rows, P, H, Hp, w, w_img_stride, x, g_x);
+    else        coord_row_grad_opt_k<T, 2><<<blocks, 256, 0, st>>>(delta0, rows, P, H, Hp, w, w_img_stride, x, g_x);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+template int coord_row_grad_opt<float>(int, const float*, int, int, int, int, const float*, long, const float*, float*,
+                                       cudaStream_t);
+template int coord_row_grad_opt<__nv_bfloat16>(int, const __nv_bfloat16*, int, int, int, int, const float*, long,
+                                               const float*, float*, cudaStream_t);
+
+}  // namespace svae

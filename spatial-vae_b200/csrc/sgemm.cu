@@ -105,6 +105,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(SgemmArgs 
             if (gn >= g.N) continue;
             float v = g.alpha * acc[i][j];
             if (g.bias != nullptr && first_split) v += __ldg(g.bias + gn);
+            if (g.add != nullptr) v += __ldg(g.add + (long)gm * g.ld_add + gn);
             if (g.act >= 0) v = act_apply<false>(g.act, v);
             if (g.dact >= 0) v *= act_deriv_from_out(g.dact, __ldg(g.dsrc + (long)gm * g.ld_dsrc + gn));
             float* c = g.C + (long)gm * g.ldc + gn;
@@ -138,7 +139,7 @@ int sgemm(const SgemmArgs& a_in, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0) return SVAE_OK;
     if (a.K <= 0) { set_error("sgemm: K must be positive"); return SVAE_EINVAL; }
     if (a.split_k > 1) {
-        if (a.act >= 0 || a.dact >= 0) { set_error("sgemm: split-K cannot carry a nonlinear epilogue"); return SVAE_EINVAL; }
+        if (a.act >= 0 || a.dact >= 0 || a.add != nullptr) { set_error("sgemm: split-K cannot carry a nonlinear epilogue"); return SVAE_EINVAL; }
         a.accumulate = 1;
     }
     const long big_tiles = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * (a.split_k > 1 ? a.split_k : 1);

@@ -928,21 +928,26 @@ __global__ void __launch_bounds__(256) latent_backward_k(SvaeShape s, SvaeConfig
                                                          int Hp, const float* __restrict__ img,
                                                          const float* __restrict__ coord_w,
                                                          const float* __restrict__ dz, const float* __restrict__ zo,
-                                                         const float* __restrict__ eps, float* __restrict__ g_zo) {
+                                                         const float* __restrict__ eps, float* __restrict__ g_zo,
+                                                         const float* __restrict__ coord_pre) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     if (b >= s.B) return;
-    const float* Sb = S + (long)b * 3 * Hp;
-    const float cs = img[b * 4], sn = img[b * 4 + 1];
     float dth = 0.f, d0 = 0.f, d1 = 0.f;
-    for (int n = lane; n < s.H; n += 32) {
-        const float w0 = coord_w[n * 2], w1 = coord_w[n * 2 + 1];
-        const float sv = Sb[n], m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
-        dth = fmaf(w0, -sn * m0 - cs * m1, fmaf(w1, cs * m0 - sn * m1, dth));
-        d0 = fmaf(w0, sv, d0);
-        d1 = fmaf(w1, sv, d1);
+    if (coord_pre != nullptr) {     // option path: already reduced by latent_coord_grad_k
+        dth = coord_pre[b * 3]; d0 = coord_pre[b * 3 + 1]; d1 = coord_pre[b * 3 + 2];
+    } else {
+        const float* Sb = S + (long)b * 3 * Hp;
+        const float cs = img[b * 4], sn = img[b * 4 + 1];
+        for (int n = lane; n < s.H; n += 32) {
+            const float w0 = coord_w[n * 2], w1 = coord_w[n * 2 + 1];
+            const float sv = Sb[n], m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
+            dth = fmaf(w0, -sn * m0 - cs * m1, fmaf(w1, cs * m0 - sn * m1, dth));
+            d0 = fmaf(w0, sv, d0);
+            d1 = fmaf(w1, sv, d1);
+        }
+        dth = warp_sum(dth); d0 = warp_sum(d0); d1 = warp_sum(d1);
     }
-    dth = warp_sum(dth); d0 = warp_sum(d0); d1 = warp_sum(d1);
     const int I = s.I, rot = c.rotate ? 1 : 0, zcol = rot + (c.translate ? 2 : 0);
     const float gs = c.grad_scale;
     for (int i = lane; i < I; i += 32) {
@@ -966,8 +971,8 @@ __global__ void __launch_bounds__(256) latent_backward_k(SvaeShape s, SvaeConfig
 }
 int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
                     const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
-                    cudaStream_t st) {
-    latent_backward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, S, Hp, img, coord_w, dz, zo, eps, g_zo);
+                    cudaStream_t st, const float* coord_pre) {
+    latent_backward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, S, Hp, img, coord_w, dz, zo, eps, g_zo, coord_pre);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }

@@ -17,6 +17,7 @@ MAX_LAYERS = 8
 ACT_TANH, ACT_LEAKYRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 LIK_BERNOULLI, LIK_GAUSS, LIK_GAUSS_FITNOISE = 0, 1, 2
 PRECISION_PARITY, PRECISION_FAST = 0, 1
+ENC_RESID = 0x100          # OR-ed into the activation argument of svae_encoder_forward/backward
 
 ACT_CODES = {"tanh": ACT_TANH, "leakyrelu": ACT_LEAKYRELU, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
 PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST}
@@ -37,13 +38,14 @@ class SvaeConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("rotate", "translate", "likelihood", "theta_kl_mean", "activation", "precision", "softplus",
                  "chunk_images")] + \
-               [(n, C.c_float) for n in ("theta_prior", "dx_scale", "z_scale", "grad_scale")]
+               [(n, C.c_float) for n in ("theta_prior", "dx_scale", "z_scale", "grad_scale")] + \
+               [(n, C.c_int32) for n in ("resid", "expand_coords", "bilinear")]
 
 
 class SvaeDecoderParams(C.Structure):
     _fields_ = [("coord_w", C.c_void_p), ("coord_b", C.c_void_p), ("latent_w", C.c_void_p),
                 ("hidden_w", C.c_void_p * MAX_LAYERS), ("hidden_b", C.c_void_p * MAX_LAYERS),
-                ("out_w", C.c_void_p), ("out_b", C.c_void_p)]
+                ("out_w", C.c_void_p), ("out_b", C.c_void_p), ("bilinear_w", C.c_void_p)]
 
 
 class SvaeEncoderParams(C.Structure):

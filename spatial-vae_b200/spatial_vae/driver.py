@@ -31,6 +31,7 @@ def _spec_for(family, p_net, rotate, translate, dx_scale, theta_prior, z_scale=1
     return SF.StepSpec(family=family, rotate=bool(rotate), translate=bool(translate), dx_scale=float(dx_scale),
                        theta_prior=float(theta_prior), z_scale=float(z_scale),
                        activation=getattr(p_net, "activation_code", 0), softplus=bool(getattr(p_net, "softplus", False)),
+                       resid=bool(getattr(p_net, "resid", False)),
                        precision=precision or getattr(p_net, "precision", None) or SF.default_precision())
 
 

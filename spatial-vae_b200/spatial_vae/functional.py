@@ -33,6 +33,20 @@ def set_default_precision(p: str) -> None:
     _DEFAULT_PRECISION = p
 
 
+def unvalidated_options_enabled() -> bool:
+    """--resid / --expand-coords / --bilinear are implemented in the library (option_kernels.cu, arithmetic checked
+    on the CPU against the oracle's autograd) but their GPU parity tests have not run on a B200 yet; until they
+    have, the host layer only evaluates such networks when SVAE_UNVALIDATED_OPTIONS=1."""
+    return os.environ.get("SVAE_UNVALIDATED_OPTIONS", "0") == "1"
+
+
+def require_validated(what: str) -> None:
+    if not unvalidated_options_enabled():
+        raise NotImplementedError(
+            f"{what}: implemented in libsvae_b200 but not yet validated on a B200 (tests/test_gpu_options.py); "
+            "set SVAE_UNVALIDATED_OPTIONS=1 to run it anyway")
+
+
 def activation_code(act) -> int:
     """nn activation class / instance / name -> SVAE_ACT_* (LeakyReLU means slope 0.01)."""
     if isinstance(act, str):
@@ -92,23 +106,33 @@ class DecoderTensors:
     hidden: List[tuple]
     out_w: torch.Tensor
     out_b: torch.Tensor
+    bilinear_w: Optional[torch.Tensor] = None      # (H, F, Z) nn.Bilinear weight (models.py:74-75)
 
     def flat(self) -> List[torch.Tensor]:
+        """Parameter order of SpatialGenerator.parameters() (models.py:69-87)."""
         out = [self.coord_w, self.coord_b]
         if self.latent_w is not None:
             out.append(self.latent_w)
+        if self.bilinear_w is not None:
+            out.append(self.bilinear_w)
         for w, b in self.hidden:
             out += [w, b]
         out += [self.out_w, self.out_b]
         return out
 
+    def layout(self) -> tuple:
+        """(has_latent, n_hidden, has_bilinear): what from_flat needs to rebuild the structure."""
+        return (self.latent_w is not None, len(self.hidden), self.bilinear_w is not None)
+
     @staticmethod
-    def from_flat(flat: Sequence[torch.Tensor], has_latent: bool, n_hidden: int) -> "DecoderTensors":
+    def from_flat(flat: Sequence[torch.Tensor], has_latent: bool, n_hidden: int,
+                  has_bilinear: bool = False) -> "DecoderTensors":
         it = iter(flat)
         cw, cb = next(it), next(it)
         lw = next(it) if has_latent else None
+        bw = next(it) if has_bilinear else None
         hidden = [(next(it), next(it)) for _ in range(n_hidden)]
-        return DecoderTensors(cw, cb, lw, hidden, next(it), next(it))
+        return DecoderTensors(cw, cb, lw, hidden, next(it), next(it), bw)
 
     def struct(self) -> L.SvaeDecoderParams:
         s = L.SvaeDecoderParams()
@@ -117,6 +141,7 @@ class DecoderTensors:
         for i, (w, b) in enumerate(self.hidden):
             s.hidden_w[i], s.hidden_b[i] = _ptr(w), _ptr(b)
         s.out_w, s.out_b = _ptr(self.out_w), _ptr(self.out_b)
+        s.bilinear_w = _ptr(self.bilinear_w)
         return s
 
 
@@ -127,16 +152,29 @@ def encoder_struct(pairs: Sequence[tuple]) -> L.SvaeEncoderParams:
     return s
 
 
+def _linears(seq) -> List[nn.Linear]:
+    """The Linear modules of a reference-shaped Sequential, ResidLinear containers unwrapped (models.py:13-21)."""
+    out = []
+    for m in seq:
+        if isinstance(m, nn.Linear):
+            out.append(m)
+        elif isinstance(getattr(m, "linear", None), nn.Linear):
+            out.append(m.linear)
+    return out
+
+
 def decoder_tensors_of(p_net) -> DecoderTensors:
     """Pull the parameter tensors out of a SpatialGenerator-shaped module (models.py:69-87)."""
-    lins = [m for m in p_net.layers if isinstance(m, nn.Linear)]
+    lins = _linears(p_net.layers)
     hidden = [(m.weight, m.bias) for m in lins[:-1]]
     lw = p_net.latent_linear.weight if hasattr(p_net, "latent_linear") else None
-    return DecoderTensors(p_net.coord_linear.weight, p_net.coord_linear.bias, lw, hidden, lins[-1].weight, lins[-1].bias)
+    bw = p_net.bilinear.weight if hasattr(p_net, "bilinear") else None
+    return DecoderTensors(p_net.coord_linear.weight, p_net.coord_linear.bias, lw, hidden, lins[-1].weight,
+                          lins[-1].bias, bw)
 
 
 def encoder_pairs_of(q_net) -> List[tuple]:
-    return [(m.weight, m.bias) for m in q_net.layers if isinstance(m, nn.Linear)]
+    return [(m.weight, m.bias) for m in _linears(q_net.layers)]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -156,8 +194,9 @@ class StepSpec:
     softplus: bool = False
     precision: str = "fast"
     chunk_images: int = 0
+    resid: bool = False                   # --resid: ResidLinear hidden layers in both networks
 
-    def config(self, C_out: int, grad_scale: float) -> L.SvaeConfig:
+    def config(self, C_out: int, grad_scale: float, dec: Optional["DecoderTensors"] = None) -> L.SvaeConfig:
         c = L.SvaeConfig()
         c.rotate, c.translate = int(bool(self.rotate)), int(bool(self.translate))
         if self.family == "particles":
@@ -172,6 +211,12 @@ class StepSpec:
         c.theta_prior, c.dx_scale = float(self.theta_prior), float(self.dx_scale)
         c.z_scale = float(self.z_scale) if self.family != "mnist" else 1.0
         c.grad_scale = float(grad_scale)
+        c.resid = int(bool(self.resid))
+        if dec is not None:        # the coordinate options are visible in the parameter shapes (models.py:65-75)
+            c.expand_coords = int(dec.coord_w.shape[1] == 5)
+            c.bilinear = int(dec.bilinear_w is not None)
+        if c.resid or c.expand_coords or c.bilinear:
+            require_validated("resid / expand_coords / bilinear networks")
         return c
 
 
@@ -207,7 +252,7 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
     k_ctf = 0 if ctf is None else int(ctf.shape[-1])
     shape = shape_of(dec, enc, B, P, Cin, spec, n_rows=n if n * n == P else 0, n_cols=n if n * n == P else 0,
                      k_ctf=k_ctf)
-    cfg = spec.config(shape.C, (1.0 / max(B, 1)) if grad_scale is None else grad_scale)
+    cfg = spec.config(shape.C, (1.0 / max(B, 1)) if grad_scale is None else grad_scale, dec)
     nbytes = C.c_size_t(0)
     L.check(L.lib.svae_workspace_bytes(C.byref(shape), C.byref(cfg), C.byref(nbytes)), "svae_workspace_bytes")
     if B == 0:   # a rank whose slice of a ragged last minibatch is empty: nothing to enqueue
@@ -249,15 +294,14 @@ class _FusedElbo(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, n_dec, aux, *params):
-        grid, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad = aux
+        grid, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad, layout = aux
         dec_flat, enc_flat = params[:n_dec], params[n_dec:]
-        has_latent = (n_dec % 2 == 1)
-        dec = DecoderTensors.from_flat([p.detach() for p in dec_flat], has_latent, (n_dec - 4 - int(has_latent)) // 2)
+        dec = DecoderTensors.from_flat([p.detach() for p in dec_flat], *layout)
         enc = [(enc_flat[i].detach(), enc_flat[i + 1].detach()) for i in range(0, len(enc_flat), 2)]
         gd = ge = None
         if need_grad:
             gflat = [torch.zeros_like(p, dtype=torch.float32) for p in params]
-            gd = DecoderTensors.from_flat(gflat[:n_dec], has_latent, len(dec.hidden))
+            gd = DecoderTensors.from_flat(gflat[:n_dec], *layout)
             ge = [(gflat[n_dec + i], gflat[n_dec + i + 1]) for i in range(0, len(enc_flat), 2)]
         stats, y_hat, _ = run_step(spec, dec, enc, grid, y, eps, y_enc=y_enc, theta_offset=theta_offset, ctf=ctf,
                                    mask=mask, grad_dec=gd, grad_enc=ge, want_y_hat=want_y_hat)
@@ -282,10 +326,11 @@ def elbo_step(spec: StepSpec, x_coord, y, p_net, q_net, *, eps=None, y_enc=None,
               mask=None, want_y_hat=False):
     """The body of eval_minibatch.  Returns (elbo, logp, kl, y_hat, per_image_stats); elbo carries
     autograd history w.r.t. the parameters of p_net and q_net."""
-    if hasattr(p_net, "_check_supported"):
-        p_net._check_supported()
-    if getattr(q_net, "resid", False):
-        raise NotImplementedError("--resid networks are not implemented in the B200 kernels yet")
+    if bool(getattr(p_net, "resid", False)) != bool(getattr(q_net, "resid", False)):
+        raise NotImplementedError("the fused step takes one resid flag for both networks, as the reference's --resid "
+                                  "does (train_particles.py:291,437-446)")
+    if bool(getattr(p_net, "resid", False)) != bool(spec.resid):
+        spec = StepSpec(**{**spec.__dict__, "resid": bool(getattr(p_net, "resid", False))})
     dec = decoder_tensors_of(p_net)
     enc = encoder_pairs_of(q_net)
     _require_cuda(x_coord, y, dec.coord_w, enc[0][0])
@@ -298,7 +343,7 @@ def elbo_step(spec: StepSpec, x_coord, y, p_net, q_net, *, eps=None, y_enc=None,
     eflat = [t for pair in enc for t in pair]
     # autograd Functions run their forward with grad mode off, so decide here whether the backward is wanted
     need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in dflat + eflat)
-    aux = (x_coord, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad)
+    aux = (x_coord, y, eps, y_enc, theta_offset, ctf, mask, want_y_hat, need_grad, dec.layout())
     elbo, logp, kl, y_hat, stats = _FusedElbo.apply(spec, len(dflat), aux, *dflat, *eflat)
     return elbo, logp, kl, (y_hat if want_y_hat else None), stats
 
@@ -346,21 +391,26 @@ class _EncoderFn(torch.autograd.Function):
 def encoder_forward(q_net, x: torch.Tensor) -> torch.Tensor:
     pairs = encoder_pairs_of(q_net)
     flat = [t for p in pairs for t in p]
-    return _EncoderFn.apply(q_net.activation_code, x, *flat)
+    act = q_net.activation_code
+    if getattr(q_net, "resid", False):
+        require_validated("resid InferenceNetwork")
+        act |= L.ENC_RESID
+    return _EncoderFn.apply(act, x, *flat)
 
 
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, x, z, *flat):
-        act, softplus, precision, has_latent = meta
+        act, softplus, precision, resid, layout = meta
         _require_cuda(x, flat[0])
-        dec = DecoderTensors.from_flat([t.detach() for t in flat], has_latent, (len(flat) - 4 - int(has_latent)) // 2)
+        dec = DecoderTensors.from_flat([t.detach() for t in flat], *layout)
         B, P = x.shape[0], x.shape[1]
         H, Cn = dec.coord_w.shape[0], dec.out_w.shape[0]
         Z = 0 if dec.latent_w is None else dec.latent_w.shape[1]
         shape = make_shape(B, P, Cn, 1, Z, Z, H, len(dec.hidden) + 1, 1, 1)
-        spec = StepSpec(rotate=False, translate=False, activation=act, softplus=softplus, precision=precision)
-        cfg = spec.config(Cn, 1.0)
+        spec = StepSpec(rotate=False, translate=False, activation=act, softplus=softplus, precision=precision,
+                        resid=resid)
+        cfg = spec.config(Cn, 1.0, dec)
         nbytes = C.c_size_t(0)
         L.check(L.lib.svae_workspace_bytes(C.byref(shape), C.byref(cfg), C.byref(nbytes)), "svae_workspace_bytes")
         ws = workspace(nbytes.value, x.device)
@@ -378,11 +428,11 @@ class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_y):
         xf, zf, *flat = ctx.saved_tensors
-        act, softplus, precision, has_latent = ctx.meta
-        dec = DecoderTensors.from_flat(flat, has_latent, (len(flat) - 4 - int(has_latent)) // 2)
+        layout = ctx.meta[4]
+        dec = DecoderTensors.from_flat(flat, *layout)
         shape, cfg = ctx.shape, ctx.cfg
         grads = [torch.zeros_like(t) for t in flat]
-        gdec = DecoderTensors.from_flat(grads, has_latent, len(dec.hidden))
+        gdec = DecoderTensors.from_flat(grads, *layout)
         nbytes = C.c_size_t(0)
         L.check(L.lib.svae_workspace_bytes(C.byref(shape), C.byref(cfg), C.byref(nbytes)), "svae_workspace_bytes")
         ws = workspace(nbytes.value, xf.device)
@@ -400,8 +450,10 @@ class _DecoderFn(torch.autograd.Function):
 
 def decoder_forward(p_net, x: torch.Tensor, z: Optional[torch.Tensor]) -> torch.Tensor:
     dec = decoder_tensors_of(p_net)
+    if getattr(p_net, "resid", False) or dec.bilinear_w is not None or dec.coord_w.shape[1] == 5:
+        require_validated("resid / expand_coords / bilinear SpatialGenerator")
     meta = (p_net.activation_code, bool(p_net.softplus), getattr(p_net, "precision", None) or default_precision(),
-            dec.latent_w is not None)
+            bool(getattr(p_net, "resid", False)), dec.layout())
     return _DecoderFn.apply(meta, x, z, *dec.flat())
 
 

@@ -4,8 +4,9 @@ Same classes, constructor arguments, attribute names and state_dict keys as the 
 module (reference spatial_vae/models.py:13-172), so whole-module `.sav` pickles and state
 dicts interchange.  The submodules only HOLD the parameters; `forward` hands them to the
 sm_100a kernels in libsvae_b200.so through `spatial_vae.functional` (no eager arithmetic, no CPU
-fallback).  Options that are not on the fused path yet (resid, expand_coords, bilinear) keep
-their parameters for compatibility and raise NotImplementedError when evaluated.
+fallback).  The options resid / expand_coords / bilinear run through option_kernels.cu; until their GPU
+parity tests have run on a B200 they are gated behind SVAE_UNVALIDATED_OPTIONS=1
+(spatial_vae.functional.require_validated).
 """
 from __future__ import annotations
 
@@ -31,8 +32,9 @@ def _stack(first_in, width, depth, act, resid):
 
 
 class ResidLinear(nn.Module):
-    """act(linear(x) + x) (reference models.py:13-21).  Parameter container only: the residual
-    variant is not on the B200 fused path yet."""
+    """act(linear(x) + x) (reference models.py:13-21).  Parameter container: the networks that own it evaluate
+    it inside their own fused forward (the skip connection rides in the GEMM epilogue, or in W + I on the
+    tensor-core path); it has no kernel of its own."""
 
     def __init__(self, n_in, n_out, activation=nn.Tanh):
         super().__init__()
@@ -40,7 +42,7 @@ class ResidLinear(nn.Module):
         self.act = activation()
 
     def forward(self, x):
-        raise NotImplementedError("--resid networks are not implemented in the B200 kernels yet")
+        raise NotImplementedError("ResidLinear is evaluated as part of InferenceNetwork / SpatialGenerator")
 
 
 class InferenceNetwork(nn.Module):
@@ -57,8 +59,6 @@ class InferenceNetwork(nn.Module):
         print(self)
 
     def forward(self, x):
-        if self.resid:
-            raise NotImplementedError("--resid networks are not implemented in the B200 kernels yet")
         out = SF.encoder_forward(self, x)
         return out[:, :self.latent_dim], out[:, self.latent_dim:]
 
@@ -87,13 +87,7 @@ class SpatialGenerator(nn.Module):
         self.precision = None     # None = spatial_vae.functional.default_precision()
         print(self)
 
-    def _check_supported(self):
-        if self.resid or self.expand_coords or hasattr(self, "bilinear"):
-            raise NotImplementedError("resid / expand_coords / bilinear decoders are not implemented in the B200 "
-                                      "kernels yet (SURVEY.md section 8f rank 2)")
-
     def forward(self, x, z):
-        self._check_supported()
         if x.dim() < 3:
             x = x.unsqueeze(0)
         if z is not None and z.dim() < 2:

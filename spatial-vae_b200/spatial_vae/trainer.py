@@ -60,8 +60,10 @@ class Trainer:
 
     def __init__(self, p_net, q_net, spec: SF.StepSpec, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  process_group=None):
-        if hasattr(p_net, "_check_supported"):
-            p_net._check_supported()
+        if bool(getattr(p_net, "resid", False)) != bool(getattr(q_net, "resid", False)):
+            raise NotImplementedError("one resid flag for both networks, as the reference's --resid")
+        if bool(getattr(p_net, "resid", False)) != bool(spec.resid):
+            spec = SF.StepSpec(**{**spec.__dict__, "resid": bool(getattr(p_net, "resid", False))})
         self.p_net, self.q_net, self.spec = p_net, q_net, spec
         self.lr, self.betas, self.adam_eps = lr, betas, eps
         self.flat = FlatParams(list(p_net.parameters()) + list(q_net.parameters()))
@@ -81,7 +83,7 @@ class Trainer:
         self.dec, self.enc = dec, enc
         n_dec = len(dec.flat())
         gv = self.flat.views(self.flat.grad)
-        self.gdec = SF.DecoderTensors.from_flat(gv[:n_dec], dec.latent_w is not None, len(dec.hidden))
+        self.gdec = SF.DecoderTensors.from_flat(gv[:n_dec], *dec.layout())
         self.genc = [(gv[n_dec + i], gv[n_dec + i + 1]) for i in range(0, len(gv) - n_dec, 2)]
 
     # -- one train step ---------------------------------------------------------------------------

@@ -72,8 +72,12 @@ load_images = D.load_particle_stack
 
 def main(argv=None):
     args = parse(argv)
-    if args.vanilla or args.resid or args.expand_coords or args.bilinear:
-        raise SystemExit('--vanilla/--resid/--expand-coords/--bilinear are not on the B200 fused path yet')
+    if args.vanilla:
+        raise SystemExit('--vanilla uses the non-spatial MLP generator, which is outside the B200 fused path; '
+                         'run it with the reference implementation')
+    if (args.resid or args.expand_coords or args.bilinear) and not SF.unvalidated_options_enabled():
+        raise SystemExit('--resid/--expand-coords/--bilinear are implemented in libsvae_b200 but their GPU parity '
+                         'tests have not run on a B200 yet; set SVAE_UNVALIDATED_OPTIONS=1 to train with them')
     if args.fit_noise and args.ctf_train is not None:
         raise SystemExit('--fit-noise cannot be combined with CTF filtering (the reference crashes on it, '
                          'train_particles.py:121-124,137)')
@@ -127,14 +131,15 @@ def main(argv=None):
     inf_dim = args.z_dim + (1 if rotate else 0) + (2 if translate else 0)
     p_net = models.SpatialGenerator(args.z_dim, args.p_hidden_dim, n_out=2 if args.fit_noise else 1,
                                     num_layers=args.p_num_layers, activation=activation,
-                                    softplus=args.softplus).to(device)
+                                    softplus=args.softplus, resid=args.resid, expand_coords=args.expand_coords,
+                                    bilinear=args.bilinear).to(device)
     q_net = models.InferenceNetwork(n * m, inf_dim, args.q_hidden_dim, num_layers=args.q_num_layers,
-                                    activation=activation).to(device)
+                                    activation=activation, resid=args.resid).to(device)
     print('# using priors: theta={}, dx={}'.format(args.theta_prior, args.dx_scale), file=sys.stderr)
 
     spec = SF.StepSpec(family='particles', rotate=rotate, translate=translate, dx_scale=args.dx_scale,
                        theta_prior=args.theta_prior, activation=p_net.activation_code, softplus=args.softplus,
-                       precision=args.precision)
+                       precision=args.precision, resid=args.resid)
     trainer = Trainer(p_net, q_net, spec, lr=args.learning_rate)
     shuffle_gen = torch.Generator().manual_seed(args.seed if args.seed is not None else 0)
     augment = None

@@ -31,12 +31,35 @@ def test_library_exports_every_declared_symbol(built):
     assert built.lib.svae_version() >= 100
 
 
-def test_struct_sizes_match_header(built):
+def test_struct_layouts_match_header(built, tmp_path):
+    """sizeof / offsetof of every struct as gcc lays out include/svae_b200.h == the ctypes mirror in _lib.py."""
     import ctypes as C
-    assert C.sizeof(built.SvaeShape) == 13 * 4
-    assert C.sizeof(built.SvaeConfig) == 12 * 4
-    assert C.sizeof(built.SvaeDecoderParams) == 8 * (3 + 2 * built.MAX_LAYERS + 2)
-    assert C.sizeof(built.SvaeEncoderParams) == 8 * 2 * (built.MAX_LAYERS + 1)
+    import subprocess
+    structs = {"SvaeShape": built.SvaeShape, "SvaeConfig": built.SvaeConfig,
+               "SvaeDecoderParams": built.SvaeDecoderParams, "SvaeEncoderParams": built.SvaeEncoderParams,
+               "SvaeStepInputs": built.SvaeStepInputs, "SvaeStepOutputs": built.SvaeStepOutputs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svae_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
+    # the header has no field the mirror lacks: count the members gcc sees through the struct sizes above and
+    # through the declarations themselves
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "svae_b200.h")).read(), flags=re.S)
+    for name, cls in structs.items():
+        body = re.search(r"typedef struct \{([^}]*)\} %s;" % name, hdr).group(1)
+        members = [m for m in body.split(";") if m.strip()]
+        assert len(members) == len(cls._fields_), (name, members)
 
 
 def test_invalid_arguments_return_error_codes_without_a_gpu(built):
@@ -92,12 +115,44 @@ def test_same_seed_gives_reference_parameter_init(built):
         np.testing.assert_array_equal(v.numpy(), d["q." + k])
 
 
-def test_unsupported_options_raise(built):
+def test_unvalidated_options_are_gated(built, monkeypatch):
+    """resid / expand_coords / bilinear run through option_kernels.cu, but only behind SVAE_UNVALIDATED_OPTIONS=1
+    until tests/test_gpu_options.py has passed on a B200; either way there is no CPU path."""
     import spatial_vae.models as M
     with contextlib.redirect_stdout(io.StringIO()):
-        p = M.SpatialGenerator(3, 16, resid=True, num_layers=2)
-    with pytest.raises(NotImplementedError):
-        p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
+        nets = [M.SpatialGenerator(3, 16, resid=True, num_layers=2), M.SpatialGenerator(3, 16, expand_coords=True),
+                M.SpatialGenerator(3, 16, bilinear=True)]
+        q = M.InferenceNetwork(8, 3, 16, num_layers=2, resid=True)
+    assert [k for k, _ in nets[2].named_parameters()][:4] == ["coord_linear.weight", "coord_linear.bias",
+                                                              "latent_linear.weight", "bilinear.weight"]
+    assert "layers.1.linear.weight" in dict(nets[0].named_parameters())
+    monkeypatch.delenv("SVAE_UNVALIDATED_OPTIONS", raising=False)
+    for p in nets:
+        with pytest.raises(NotImplementedError, match="SVAE_UNVALIDATED_OPTIONS"):
+            p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
+    with pytest.raises(NotImplementedError, match="SVAE_UNVALIDATED_OPTIONS"):
+        q(torch.zeros(2, 8))
+    monkeypatch.setenv("SVAE_UNVALIDATED_OPTIONS", "1")
+    for p in nets:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q(torch.zeros(2, 8))
+
+
+def test_decoder_tensor_layout_follows_parameter_order(built):
+    import spatial_vae.models as M
+    import spatial_vae.functional as SF
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=2, num_layers=3, resid=True, expand_coords=True, bilinear=True)
+    dec = SF.decoder_tensors_of(p)
+    assert [t.data_ptr() for t in dec.flat()] == [t.data_ptr() for t in p.parameters()]
+    assert dec.layout() == (True, 2, True) and tuple(dec.bilinear_w.shape) == (16, 5, 3)
+    again = SF.DecoderTensors.from_flat(dec.flat(), *dec.layout())
+    assert [t.data_ptr() for t in again.flat()] == [t.data_ptr() for t in dec.flat()]
+    with contextlib.redirect_stdout(io.StringIO()):
+        q = M.InferenceNetwork(8, 3, 16, num_layers=3, resid=True)
+    assert [t.data_ptr() for pr in SF.encoder_pairs_of(q) for t in pr] == [t.data_ptr() for t in q.parameters()]
 
 
 def test_rotation_matrices_match_pillow_recipe(built):

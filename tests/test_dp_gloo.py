@@ -35,11 +35,16 @@ def _install_doubles(SF):
         if B == 0:
             return torch.zeros(0, 3), None, None
         cfg = O.StepConfig(family=spec.family, rotate=spec.rotate, translate=spec.translate, dx_scale=spec.dx_scale,
-                           theta_prior=spec.theta_prior, z_scale=spec.z_scale)
+                           theta_prior=spec.theta_prior, z_scale=spec.z_scale, softplus=spec.softplus,
+                           resid=spec.resid)
         d = {"coord_w": dec.coord_w.detach(), "coord_b": dec.coord_b.detach(),
              "latent_w": dec.latent_w.detach() if dec.latent_w is not None else None,
              "hidden": [(w.detach(), b.detach()) for w, b in dec.hidden], "out_w": dec.out_w.detach(),
              "out_b": dec.out_b.detach()}
+        if dec.bilinear_w is not None:
+            d["bilinear_w"] = dec.bilinear_w.detach()
+        if spec.resid:
+            d["resid"] = True
         e = [(w.detach(), b.detach()) for w, b in enc]
         out, grads = O.step_grads(cfg, d, e, grid, y, eps)
         if grad_dec is not None:
@@ -138,3 +143,37 @@ def test_shard_bounds_cover_and_are_contiguous():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= max(1, (n + w - 1) // w)
+
+
+def test_trainer_host_logic_with_every_option(monkeypatch):
+    """Single process, library calls replaced by the oracle doubles: the flat parameter / gradient views must line
+    up with the parameter order of a resid + expand_coords + bilinear + softplus network pair
+    (coord W,b; latent W; bilinear W; layers.N.linear W,b; out W,b; then the encoder), so that 5 trainer steps
+    equal 5 oracle steps."""
+    import spatial_vae.functional as SF
+    import spatial_vae.models as M
+    from spatial_vae.trainer import Trainer
+    monkeypatch.setattr(SF, "run_step", SF.run_step)
+    monkeypatch.setattr(SF, "adam_step_graph", SF.adam_step_graph)
+    _install_doubles(SF)
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=2, num_layers=3, resid=True, expand_coords=True, bilinear=True,
+                               softplus=True)
+        q = M.InferenceNetwork(36, 6, 12, num_layers=3, resid=True)
+    dec0 = O.decoder_params_from_state({k: v.detach().clone() for k, v in p.state_dict().items()})
+    enc0 = O.encoder_params_from_state({k: v.detach().clone() for k, v in q.state_dict().items()})
+    assert dec0["coord_w"].shape[1] == 5 and dec0["bilinear_w"] is not None and dec0.get("resid")
+    spec = SF.StepSpec(family="particles", theta_prior=0.9, precision="parity", softplus=True, z_scale=0.5)
+    tr = Trainer(p, q, spec, lr=1e-3)
+    assert tr.spec.resid                               # picked up from the networks
+    grid = O.make_grid(6, 6)
+    g = torch.Generator().manual_seed(2)
+    ys = [torch.randn(4, 36, generator=g) for _ in range(5)]
+    eps = [torch.randn(4, 6, generator=g) for _ in range(5)]
+    for y, e in zip(ys, eps):
+        tr.step(grid, y, eps=e)
+    cfg = O.StepConfig(family="particles", theta_prior=0.9, softplus=True, resid=True, z_scale=0.5)
+    dec_o, enc_o, _ = O.train_steps(cfg, dec0, enc0, grid, ys, eps, lr=1e-3)
+    for t, r in zip(list(p.parameters()) + list(q.parameters()), O.flatten_params(dec_o, enc_o)):
+        np.testing.assert_allclose(t.detach().numpy(), r.numpy(), rtol=1e-5, atol=1e-6)
