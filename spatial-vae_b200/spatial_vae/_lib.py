@@ -65,7 +65,11 @@ def _load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (or `make -C spatial-vae_b200/csrc`). "
             "spatial_vae (B200) has no CPU or eager fallback.")
-    lib = C.CDLL(LIB_PATH)
+    return declare(C.CDLL(LIB_PATH))
+
+
+def declare(lib):
+    """Attach the argument / return types of include/svae_b200.h to a loaded library object."""
     vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     P = C.POINTER
     lib.svae_version.restype = i32

@@ -19,3 +19,26 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+# ---- SVAE_TEST_BACKEND=emu: run the bodies of the `gpu` tests on the CPU against tests/simt_emu -------------------
+# (the library's SIMT kernel sources compiled for the host; see tests/simt_emu/cuda_emu.h).  Used by
+# tests/test_emu_gpu_suite.py to execute, before any GPU time is spent, the very tests the B200 box will run.
+# Not a product mode: the package itself never loads the host build.
+EMU_BACKEND = os.environ.get("SVAE_TEST_BACKEND") == "emu"
+
+
+@pytest.fixture(autouse=True)
+def _emu_backend(request, monkeypatch):
+    if not EMU_BACKEND or request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+    from tests import emu_backend
+    emu_backend.install(monkeypatch)
+    cpu = torch.device("cpu")
+    if hasattr(request.module, "_cuda"):
+        monkeypatch.setattr(request.module, "_cuda", lambda: cpu)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    yield

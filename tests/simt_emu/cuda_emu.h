@@ -1,0 +1,176 @@
+// SIMT-on-host shim for UNIT-TESTING the library's CUDA C++ kernel sources without a GPU.
+//
+// TEST INFRASTRUCTURE ONLY.  tests/simt_emu/build.py rewrites the launch syntax of spatial-vae_b200/csrc/*.cu
+// (everything except the tcgen05 file) and compiles the SAME kernel bodies with g++ against this header into
+// tests/simt_emu/_build/libsvae_emu.so, which tests/ load through the same C ABI to check indexing, reductions and
+// the host orchestration on tiny inputs.  Nothing in the package, bench.py or __graft_entry__ knows about it; the
+// product has no CPU path.
+//
+// Execution model: one OS thread.  A launch runs its blocks one after another; the threads of a block are
+// ucontext fibers scheduled round-robin, yielding only at __syncthreads() (block barrier) and at warp shuffles
+// (per-warp barrier), so static __shared__ arrays are simply function-local statics and atomics are plain adds.
+// Finished threads count as arrived at every barrier (the CUDA rule for exited threads).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <type_traits>
+#include <vector>
+
+// ---- qualifiers ---------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define SVAE_SIMT_EMU 1
+
+// ---- vector types ---------------------------------------------------------------------------------
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
+// ---- bf16 (round to nearest even, like the _rn intrinsics) --------------------------------------------------
+struct __nv_bfloat16 { uint16_t bits; };
+struct alignas(4) __nv_bfloat162 { __nv_bfloat16 x, y; };   // x = low half
+inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    __nv_bfloat16 r;
+    if ((u & 0x7fffffffu) > 0x7f800000u) { r.bits = (uint16_t)((u >> 16) | 0x40); return r; }   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    r.bits = (uint16_t)(u >> 16);
+    return r;
+}
+inline float __bfloat162float(__nv_bfloat16 h) {
+    uint32_t u = (uint32_t)h.bits << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) {
+    return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)};
+}
+inline float __low2float(__nv_bfloat162 v) { return __bfloat162float(v.x); }
+inline float __high2float(__nv_bfloat162 v) { return __bfloat162float(v.y); }
+
+// ---- runtime types ---------------------------------------------------------------------------------
+typedef struct CUstream_st* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+// ---- built-in variables and the fiber scheduler ------------------------------------------------------
+namespace svae_emu {
+
+struct State {
+    enum { RUNNABLE, WAIT_BLOCK, WAIT_WARP, DONE };
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::vector<int> status;
+    std::vector<char*> stacks;
+    std::vector<float> shfl;          // one exchange slot per thread
+    std::function<void()>* body = nullptr;
+    int n = 0, cur = 0;
+    void* dyn = nullptr;
+    size_t dyn_cap = 0;
+};
+State& state();
+void yield(int why);
+void run_block(std::function<void()>& body, int nthreads);
+void* dyn_smem();
+unsigned long long globaltimer();
+
+}  // namespace svae_emu
+
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+
+inline void __syncthreads() { svae_emu::yield(svae_emu::State::WAIT_BLOCK); }
+inline void __syncwarp(unsigned = 0xffffffffu) { svae_emu::yield(svae_emu::State::WAIT_WARP); }
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    svae_emu::State& s = svae_emu::state();
+    const int me = s.cur;
+    s.shfl[me] = v;
+    svae_emu::yield(svae_emu::State::WAIT_WARP);
+    const int partner = (me & ~31) | ((me & 31) ^ lane_mask);
+    const float r = (partner < s.n) ? s.shfl[partner] : v;
+    svae_emu::yield(svae_emu::State::WAIT_WARP);
+    return r;
+}
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }
+inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
+inline long long clock64() { return (long long)(svae_emu::globaltimer() * 2); }   // "2 GHz"
+
+// round-to-nearest single operations (the build uses -ffp-contract=off, so plain operators are exactly these)
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+
+template <typename A, typename B> inline typename std::common_type<A, B>::type min(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)a < (T)b ? (T)a : (T)b;
+}
+template <typename A, typename B> inline typename std::common_type<A, B>::type max(A a, B b) {
+    typedef typename std::common_type<A, B>::type T;
+    return (T)a > (T)b ? (T)a : (T)b;
+}
+
+// ---- launches: kernel<<<grid, block, smem, stream>>>(args...) is rewritten by build.py into
+//      svae_emu::Launcher(grid, block, smem, stream).run(kernel, args...) ---------------------------------------
+namespace svae_emu {
+struct Launcher {
+    dim3 g, b;
+    size_t smem;
+    Launcher(dim3 g_, dim3 b_, size_t smem_ = 0, cudaStream_t = nullptr) : g(g_), b(b_), smem(smem_) {}
+    template <typename... P, typename... A>
+    void run(void (*k)(P...), A&&... a) {
+        State& s = state();
+        if (smem > s.dyn_cap) {
+            free(s.dyn);
+            s.dyn = aligned_alloc(128, (smem + 127) / 128 * 128);
+            s.dyn_cap = smem;
+        }
+        std::function<void()> body = [&]() { k(a...); };
+        gridDim = g;
+        blockDim = b;
+        for (unsigned z = 0; z < g.z; ++z)
+            for (unsigned y = 0; y < g.y; ++y)
+                for (unsigned x = 0; x < g.x; ++x) {
+                    blockIdx = uint3{x, y, z};
+                    run_block(body, (int)(b.x * b.y * b.z));
+                }
+    }
+};
+}  // namespace svae_emu
