@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of round 2 (one GPU): everything that was written after round 1's GPU budget ran out.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_round2_first.sh'
+# 1. the validated suite must still be green (two null-guarded branches were added to validated kernels);
+# 2. the option kernels + softplus / activation tests that have only run under tests/simt_emu so far;
+# 3. the register-tiled 39x39 CTF kernel: parity, then A/B on the C5 bench config.
+mkdir -p gpurun_out
+set -o pipefail
+{
+  echo "== validated suite"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+  echo "== unvalidated tests"; SVAE_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_zz_options.py tests/test_gpu_parity.py -m gpu -q -k "option or softplus or activation_variants" 2>&1 | tail -15
+  echo "== CTF fast kernel parity"; SVAE_CTF_FAST=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "ctf" 2>&1 | tail -5
+  echo "== C5 bench A (default CTF kernel) / B (SVAE_CTF_FAST=1)"
+  for v in 0 1; do
+    SVAE_CTF_FAST=$v timeout 300 python bench.py --config c5 --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ctf_fast=$v', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
+  done
+} | tee gpurun_out/round2_first.log

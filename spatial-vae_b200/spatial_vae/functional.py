@@ -43,7 +43,7 @@ def unvalidated_options_enabled() -> bool:
 def require_validated(what: str) -> None:
     if not unvalidated_options_enabled():
         raise NotImplementedError(
-            f"{what}: implemented in libsvae_b200 but not yet validated on a B200 (tests/test_gpu_options.py); "
+            f"{what}: implemented in libsvae_b200 but not yet validated on a B200 (tests/test_gpu_zz_options.py); "
             "set SVAE_UNVALIDATED_OPTIONS=1 to run it anyway")
 
 

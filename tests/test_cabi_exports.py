@@ -117,7 +117,7 @@ def test_same_seed_gives_reference_parameter_init(built):
 
 def test_unvalidated_options_are_gated(built, monkeypatch):
     """resid / expand_coords / bilinear run through option_kernels.cu, but only behind SVAE_UNVALIDATED_OPTIONS=1
-    until tests/test_gpu_options.py has passed on a B200; either way there is no CPU path."""
+    until tests/test_gpu_zz_options.py has passed on a B200; either way there is no CPU path."""
     import spatial_vae.models as M
     with contextlib.redirect_stdout(io.StringIO()):
         nets = [M.SpatialGenerator(3, 16, resid=True, num_layers=2), M.SpatialGenerator(3, 16, expand_coords=True),

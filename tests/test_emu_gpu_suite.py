@@ -1,0 +1,24 @@
+"""Runs the bodies of the `-m gpu` tests on the CPU against tests/simt_emu (SVAE_TEST_BACKEND=emu, see
+tests/conftest.py): the very tests the B200 box executes at round end, minus the ones that are too large for a
+fiber-based emulation or that need real CUDA machinery (tcgen05 GEMM unit tests, CUDA graphs, full-size shapes).
+One subprocess, so the emulation patches never leak into the other CPU tests."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# too large for the emulation (minutes) or meaningless on it (they unit-test the tcgen05 kernel, which the
+# emulation replaces by a plain-loop stand-in; CUDA graphs do not exist on a host)
+DESELECT = "not tc_gemm and not c1_shape and not c2_full_size and not full_model_size and not graphed_step"
+
+
+def test_gpu_test_bodies_pass_on_the_simt_emulation():
+    env = dict(os.environ, SVAE_TEST_BACKEND="emu")
+    env.pop("SVAE_CTF_FAST", None)
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_api.py", "tests/test_gpu_parity.py",
+           "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", DESELECT]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:])
+    assert r.returncode == 0, tail
+    assert " passed" in tail and " failed" not in tail and " skipped" not in tail, tail
