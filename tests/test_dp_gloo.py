@@ -69,14 +69,18 @@ def _install_doubles(SF):
     SF.adam_step_graph = fake_adam
 
 
-def _worker(rank, world, port, batches, tmp):
+def _worker(rank, world, port, batches, tmp, backend="doubles"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import spatial_vae.functional as SF
         import spatial_vae.models as M
         from spatial_vae.trainer import Trainer, shard_bounds
-        _install_doubles(SF)
+        if backend == "doubles":
+            _install_doubles(SF)
+        else:       # the library's own kernel sources, compiled for the host (tests/simt_emu)
+            from tests import emu_backend
+            emu_backend.install(pytest.MonkeyPatch())
         torch.manual_seed(3)
         with contextlib.redirect_stdout(io.StringIO()):
             p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2)
@@ -111,10 +115,17 @@ def _batches():
     return out
 
 
-def test_two_rank_trainer_matches_single_process_oracle(tmp_path):
+@pytest.mark.parametrize("backend", ["doubles", "simt_emu"])
+def test_two_rank_trainer_matches_single_process_oracle(tmp_path, backend):
+    """backend "doubles": library calls replaced by oracle-backed doubles (pure host logic); "simt_emu": the real
+    svae_step / Adam entry points running the kernel sources on the CPU, so the per-rank grad_scale, the ragged and
+    empty shards and the gradient allreduce are checked through the C ABI itself."""
     batches = _batches()
     tmp = str(tmp_path / "dp.pt")
-    mp.spawn(_worker, args=(2, _free_port(), batches, tmp), nprocs=2, join=True)
+    if backend == "simt_emu":
+        from tests.simt_emu.build import build
+        build()                                  # compile once here, not concurrently in both ranks
+    mp.spawn(_worker, args=(2, _free_port(), batches, tmp, backend), nprocs=2, join=True)
     got = torch.load(tmp)
 
     # single-process oracle trajectory on the full minibatches, from the same initial parameters
