@@ -37,6 +37,7 @@ def install(monkeypatch, fresh_copy_dir=None):
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes) + 4096, dtype=torch.uint8)
             buffers["ws"] = ws
+        ws.fill_(0xFF)        # NaN in fp32 and bf16: a kernel that reads scratch it never wrote poisons the result
         return ws
 
     monkeypatch.setattr(SF, "workspace", workspace)

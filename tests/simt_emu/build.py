@@ -16,7 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "spatial-vae_b200", "csrc")
-BUILD = os.path.join(HERE, "_build")
+ASAN = os.environ.get("SVAE_EMU_ASAN") == "1"      # out-of-bounds hunting: run python with LD_PRELOAD=libasan.so
+BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 OUT = os.path.join(BUILD, "libsvae_emu.so")
 SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
@@ -62,6 +63,10 @@ def build(force: bool = False) -> str:
     units += [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(HERE, "tc_gemm_ref.cpp")]
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
              "-I", os.path.join(HERE, "include"), "-I", BUILD, "-I", HERE]
+    link = []
+    if ASAN:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"]
+        link = ["-fsanitize=address"]
     objs = []
     procs = []
     for u in units:
@@ -72,7 +77,7 @@ def build(force: bool = False) -> str:
         _, err = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"g++ failed on {u}:\n{err[-4000:]}")
-    subprocess.run(["g++", "-shared", "-o", OUT, *objs], check=True)
+    subprocess.run(["g++", "-shared", *link, "-o", OUT, *objs], check=True)
     return OUT
 
 
