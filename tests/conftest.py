@@ -33,26 +33,9 @@ def _emu_backend(request, monkeypatch):
     if not EMU_BACKEND or request.node.get_closest_marker("gpu") is None:
         yield
         return
-    import torch
     from tests import emu_backend
-    emu_backend.install(monkeypatch)
-    cpu = torch.device("cpu")
+    cpu = emu_backend.install_all(monkeypatch)
     for helper in ("_cuda", "_dev"):
         if hasattr(request.module, helper):
             monkeypatch.setattr(request.module, helper, lambda: cpu)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-
-    class _Event:
-        def __init__(self, *a, **k): pass
-        def record(self, *a, **k): pass
-        def synchronize(self): pass
-        def elapsed_time(self, other): return 0.0
-
-    monkeypatch.setattr(torch.cuda, "Event", _Event)
-    import spatial_vae.driver as D
-    monkeypatch.setattr(D, "pick_device", lambda *a, **k: cpu)
-    from spatial_vae.trainer import Trainer
-    monkeypatch.setattr(Trainer, "step_graphed", lambda self, *a, **k: self.step(*a, **k))   # no CUDA graphs on a host
     yield

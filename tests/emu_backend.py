@@ -43,3 +43,26 @@ def install(monkeypatch, fresh_copy_dir=None):
     monkeypatch.setattr(SF, "workspace", workspace)
     monkeypatch.setenv("SVAE_UNVALIDATED_OPTIONS", "1")
     return emu
+
+
+def install_all(monkeypatch, fresh_copy_dir=None):
+    """install() plus stand-ins for the CUDA-only HOST machinery the drivers use (device selection, pinned memory,
+    events, CUDA graphs), so that whole command lines can run on the emulation.  Returns the CPU device."""
+    install(monkeypatch, fresh_copy_dir)
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+
+    class _Event:
+        def __init__(self, *a, **k): pass
+        def record(self, *a, **k): pass
+        def synchronize(self): pass
+        def elapsed_time(self, other): return 0.0
+
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    import spatial_vae.driver as D
+    monkeypatch.setattr(D, "pick_device", lambda *a, **k: cpu)
+    from spatial_vae.trainer import Trainer
+    monkeypatch.setattr(Trainer, "step_graphed", lambda self, *a, **k: self.step(*a, **k))   # no CUDA graphs on a host
+    return cpu

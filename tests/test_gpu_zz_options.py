@@ -199,7 +199,8 @@ def test_option_trainer_trajectory_matches_oracle():
 
 def test_particles_command_line_with_every_option():
     """train_particles.py --resid --expand-coords --bilinear --softplus --fit-noise on synthetic data: two epochs,
-    finite and improving ELBO (the flags reach the networks, the trainer and the fused step)."""
+    finite ELBO, and the training ELBO improves at a learning rate where six steps are enough to see it (the flags
+    reach the networks, the trainer and the fused step)."""
     import importlib.util
     import math
     _cuda()
@@ -209,7 +210,7 @@ def test_particles_command_line_with_every_option():
     spec.loader.exec_module(mod)
     argv = ["--synthetic", "96", "--synthetic-size", "12", "--num-epochs", "2", "--minibatch-size", "40",
             "--p-hidden-dim", "64", "--p-num-layers", "3", "--q-hidden-dim", "64", "--q-num-layers", "3", "--fit-noise",
-            "--resid", "--expand-coords", "--bilinear", "--softplus", "--seed", "0"]
+            "--resid", "--expand-coords", "--bilinear", "--softplus", "--seed", "0", "-l", "0.003"]
     with contextlib.redirect_stdout(io.StringIO()) as buf:
         mod.main(argv)
     lines = [l for l in buf.getvalue().splitlines() if "\t" in l]
