@@ -815,12 +815,14 @@ int svae_adam_step_graph(float* param, float* grad, float* m, float* v, size_t n
 
 int svae_gather_rows(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t row_len,
                      void* stream) {
+    if (n_rows == 0) return SVAE_OK;       // an empty slice (a rank with no images in a ragged minibatch)
     SVAE_REQUIRE(src && index && dst, SVAE_EINVAL, "null argument");
     return gather_rows(src, index, dst, n_rows, row_len, (cudaStream_t)stream);
 }
 
 int svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, const int32_t* mode, int B, int n_rows,
                         int n_cols, int channels, int quantize_u8, void* stream) {
+    if (B == 0) return SVAE_OK;
     SVAE_REQUIRE(src && dst && inv_affine && mode, SVAE_EINVAL, "null argument");
     SVAE_REQUIRE(B >= 0 && n_rows > 0 && n_cols > 0 && channels >= 1 && channels <= 4, SVAE_EINVAL, "bad image shape");
     return rotate_bicubic(src, dst, inv_affine, mode, B, n_rows, n_cols, channels, quantize_u8, (cudaStream_t)stream);
@@ -834,6 +836,7 @@ static double round15(double x) {
 }
 
 int svae_rotation_matrices(const double* angles_deg, int B, int n_rows, int n_cols, double* inv_affine, int32_t* mode) {
+    if (B == 0) return SVAE_OK;
     SVAE_REQUIRE(angles_deg && inv_affine && mode && B >= 0, SVAE_EINVAL, "null argument");
     const double cx = n_cols / 2.0, cy = n_rows / 2.0;
     for (int b = 0; b < B; ++b) {

@@ -486,6 +486,8 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tens
     idx = index.to(torch.int64).contiguous()
     if out is None:
         out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    if idx.numel() == 0:          # empty tensors have a NULL data_ptr: nothing to enqueue
+        return out
     L.check(L.lib.svae_gather_rows(src2.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), src2.shape[1],
                                    _stream()), "svae_gather_rows")
     return out
@@ -503,6 +505,8 @@ def rotate_bicubic(y: torch.Tensor, n_rows: int, n_cols: int, angles_deg, channe
     builds them exactly as PIL/Image.py does."""
     _require_cuda(y)
     B = y.shape[0]
+    if B == 0:                    # a rank whose slice of a ragged minibatch is empty
+        return y.clone()
     ang = torch.as_tensor(angles_deg, dtype=torch.float64).contiguous()
     # a small ring of pinned staging buffers per batch size: the async copies of earlier calls may still be
     # queued behind GPU work while the host already fills the next set
