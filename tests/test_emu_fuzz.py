@@ -1,0 +1,113 @@
+"""Seeded random configurations of the fused step (shapes, depths, flags, options) on tests/simt_emu against the
+oracle: per-image ELBO and every gradient in PARITY precision, per-image ELBO in FAST.  Covers corners the fixtures
+do not: L = 1 (no hidden layer), Z = 0 (no latent), odd hidden widths (padded fp32 rows), non-square pixel counts,
+B = 1, C = 3 Bernoulli, every activation, masks, CTF kernels, augmentation offsets, chunking, and the decoder/encoder
+options in combination."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svae_oracle as O
+from tests import emu_backend
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    return emu_backend.install(monkeypatch)
+
+
+def _draw(seed):
+    r = np.random.default_rng(seed)
+    family = ["mnist", "particles", "galaxy"][seed % 3]
+    cfg = dict(family=family, B=int(r.integers(1, 6)), H=int(r.choice([7, 16, 33, 64, 70])), L=int(r.integers(1, 5)),
+               Z=int(r.choice([0, 1, 3, 5])), Hq=int(r.choice([9, 16, 24])), Lq=int(r.integers(1, 4)),
+               rotate=bool(r.integers(0, 2)), translate=bool(r.integers(0, 2)),
+               act=str(r.choice(["tanh", "leakyrelu", "relu", "sigmoid"])), chunk=int(r.choice([0, 1, 2])),
+               softplus=False, resid=bool(r.integers(0, 4) == 0), expand=bool(r.integers(0, 3) == 0),
+               bilinear=bool(r.integers(0, 3) == 0), mask=False, C=1)
+    if family == "galaxy":
+        cfg.update(n_rows=4, n_cols=4, C=3)
+    elif family == "particles":
+        cfg.update(n_rows=6, n_cols=6, C=int(r.choice([1, 2])), softplus=bool(r.integers(0, 2)),
+                   mask=bool(r.integers(0, 2)), ctf=bool(r.integers(0, 2)), augment=bool(r.integers(0, 2)))
+        if cfg["ctf"]:
+            cfg["C"] = 1                     # the reference cannot combine CTF with fit-noise
+    else:
+        cfg.update(n_rows=int(r.choice([4, 5])), n_cols=int(r.choice([5, 6])))       # non-square images
+    if cfg["Z"] == 0:
+        cfg["bilinear"] = False
+    return cfg
+
+
+def _params(c, seed):
+    g = torch.Generator().manual_seed(500 + seed)
+    rnd = lambda *s, sc=0.4: torch.randn(*s, generator=g) * sc
+    F = 5 if c["expand"] else 2
+    H, Z, P = c["H"], c["Z"], c["n_rows"] * c["n_cols"]
+    Cin = 3 if c["family"] == "galaxy" else 1
+    I = Z + int(c["rotate"]) + 2 * int(c["translate"])
+    dec = {"coord_w": rnd(H, F), "coord_b": rnd(H, sc=0.1), "latent_w": rnd(H, Z) if Z > 0 else None,
+           "hidden": [(rnd(H, H, sc=1.0 / math.sqrt(H)), rnd(H, sc=0.1)) for _ in range(c["L"] - 1)],
+           "out_w": rnd(c["C"], H, sc=1.0 / math.sqrt(H)), "out_b": rnd(c["C"], sc=0.1)}
+    if c["bilinear"]:
+        dec["bilinear_w"] = rnd(H, F, Z, sc=0.2)
+    if c["resid"]:
+        dec["resid"] = True
+    Hq = c["Hq"]
+    enc = [(rnd(Hq, P * Cin, sc=1.0 / math.sqrt(P * Cin)), rnd(Hq, sc=0.1))]
+    enc += [(rnd(Hq, Hq, sc=1.0 / math.sqrt(Hq)), rnd(Hq, sc=0.1)) for _ in range(c["Lq"] - 1)]
+    enc += [(rnd(2 * I, Hq, sc=0.3 / math.sqrt(Hq)), rnd(2 * I, sc=0.05))]
+    y = torch.rand(c["B"], P, 3, generator=g) if Cin == 3 else \
+        (torch.rand(c["B"], P, generator=g) if c["family"] == "mnist" else torch.randn(c["B"], P, generator=g))
+    eps = torch.randn(c["B"], I, generator=g)
+    mask = (torch.rand(P, generator=g) > 0.3) if c["mask"] else None
+    kw = {"mask": mask}
+    if c.get("ctf"):
+        kw["ctf"] = 0.1 * torch.randn(c["B"], 1, 5, 5, generator=g)
+    if c.get("augment") and c["rotate"]:
+        kw["theta_offset"] = torch.rand(c["B"], generator=g) * 6.28
+        kw["y_enc"] = torch.randn(c["B"], P, generator=g)
+    return dec, enc, y, eps, kw, I
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_configuration_matches_oracle(emu, seed):
+    import spatial_vae.functional as SF
+    from spatial_vae import _lib as L
+    c = _draw(seed)
+    dec, enc, y, eps, kw, I = _params(c, seed)
+    if I == 0:
+        pytest.skip("no latent at all: the reference cannot build this network either")
+    grid = O.make_grid(c["n_rows"], c["n_cols"])
+    cfg = O.StepConfig(family=c["family"], rotate=c["rotate"], translate=c["translate"], theta_prior=0.9, dx_scale=0.2,
+                       z_scale=0.7 if c["family"] != "mnist" else 1.0, activation=c["act"], softplus=c["softplus"],
+                       resid=c["resid"])
+    out, ograds = O.step_grads(cfg, dec, enc, grid, y, eps, **kw)
+    ref = (out["logp_i"] - out["kl_i"]).numpy()
+    for precision in ("parity", "fast"):
+        d = SF.DecoderTensors(dec["coord_w"].clone(), dec["coord_b"].clone(),
+                              dec["latent_w"].clone() if dec["latent_w"] is not None else None,
+                              [(w.clone(), b.clone()) for w, b in dec["hidden"]], dec["out_w"].clone(),
+                              dec["out_b"].clone(), dec["bilinear_w"].clone() if c["bilinear"] else None)
+        e = [(w.clone(), b.clone()) for w, b in enc]
+        gd = SF.DecoderTensors.from_flat([torch.zeros_like(t) for t in d.flat()], *d.layout())
+        ge = [(torch.zeros_like(w), torch.zeros_like(b)) for w, b in e]
+        spec = SF.StepSpec(family=c["family"], rotate=c["rotate"], translate=c["translate"], theta_prior=0.9,
+                           dx_scale=0.2, z_scale=0.7, activation=L.ACT_CODES[c["act"]], softplus=c["softplus"],
+                           precision=precision, chunk_images=c["chunk"], resid=c["resid"])
+        kw_lib = dict(kw)
+        if "ctf" in kw_lib:
+            kw_lib["ctf"] = kw_lib["ctf"].reshape(c["B"], 5, 5)
+        stats, _, _ = SF.run_step(spec, d, e, grid, y, eps, grad_dec=gd, grad_enc=ge, **kw_lib)
+        got = stats[:, 2].numpy()
+        scale = np.maximum(np.abs(ref), 1.0)
+        tol = 3e-5 if precision == "parity" else 1e-2
+        assert (np.abs(got - ref) / scale).max() <= tol, (c, precision, got, ref)
+        if precision == "parity":
+            grads = gd.flat() + [t for pr in ge for t in pr]
+            assert len(grads) == len(ograds)
+            for i, (a, b) in enumerate(zip(grads, ograds)):
+                lim = 2e-3 * float(b.abs().max()) + 2e-6
+                assert float((a - b).abs().max()) <= lim, (c, i, float((a - b).abs().max()), lim)
