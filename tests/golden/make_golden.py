@@ -244,7 +244,33 @@ def ctf_case(name, N=3, n=7, m=7):
                         **{c: tab[c].to_numpy() for c in tab.columns})
 
 
+def cli_defaults_case(name):
+    """Every command-line flag of the three reference drivers with its default value (repr), read from the reference's
+    own argparse parsers: train_mnist.mnist_arguments, train_galaxy.galaxy_arguments, and the parser that
+    train_particles.main builds inline (train_particles.py:277-318; its block is executed as written)."""
+    import argparse
+    import json
+    out = {}
+    old = sys.argv
+    try:
+        sys.argv = ["train_mnist.py"]
+        out["train_mnist"] = {k: repr(v) for k, v in vars(train_mnist.mnist_arguments()).items()}
+        sys.argv = ["train_galaxy.py", "train.npy", "test.npy"]
+        out["train_galaxy"] = {k: repr(v) for k, v in vars(train_galaxy.galaxy_arguments()).items()}
+    finally:
+        sys.argv = old
+    src = open(os.path.join(REF, "train_particles.py")).read()
+    block = src[src.index("parser = argparse.ArgumentParser"):src.index("args = parser.parse_args()")]
+    block = "\n".join(l[4:] if l.startswith("    ") else l for l in block.splitlines())
+    ns = {"argparse": argparse, "np": np}
+    exec(block, ns)
+    out["train_particles"] = {k: repr(v) for k, v in vars(ns["parser"].parse_args(["train.npy", "test.npy"])).items()}
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    cli_defaults_case("cli_defaults")
     mnist_case("mnist_rt", True, True)
     mnist_case("mnist_r", True, False, seed=11)
     mnist_case("mnist_t", False, True, seed=12)

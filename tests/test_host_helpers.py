@@ -133,3 +133,26 @@ def test_particle_preprocessing_matches_reference_recipes(tmp_path):
     with open(tmp_path / "stack.mrcs", "wb") as f:
         M.write(f, imgs)
     assert np.array_equal(D.load_particle_stack(str(tmp_path / "stack.mrcs")), imgs)
+
+
+def test_command_line_flags_and_defaults_match_the_reference():
+    """tests/golden/cli_defaults.json holds every flag of the reference's three argparse parsers with its default
+    (written by tests/golden/make_golden.py from the reference itself): the mirrors accept the same flags with the same
+    defaults, plus five of their own."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "cli_defaults.json")))
+    parsers = {"train_mnist": ("mnist_arguments", []), "train_particles": ("parse", ["train.npy", "test.npy"]),
+               "train_galaxy": ("galaxy_arguments", ["train.npy", "test.npy"])}
+    for name, (fn, argv) in parsers.items():
+        spec = importlib.util.spec_from_file_location("cli_defaults_" + name,
+                                                      os.path.join(root, "spatial-vae_b200", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mine = {k: repr(v) for k, v in vars(getattr(mod, fn)(argv)).items()}
+        assert ref[name], name
+        for k, v in ref[name].items():
+            assert mine.get(k) == v, (name, k, v, mine.get(k))
+        assert sorted(set(mine) - set(ref[name])) == ["precision", "seed", "synthetic", "synthetic_size", "yes"]
