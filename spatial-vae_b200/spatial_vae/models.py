@@ -45,17 +45,33 @@ class ResidLinear(nn.Module):
         raise NotImplementedError("ResidLinear is evaluated as part of InferenceNetwork / SpatialGenerator")
 
 
-class InferenceNetwork(nn.Module):
+class _Derived:
+    """What the kernels need to know beyond the parameters is READ OFF the module structure instead of being stored,
+    so that whole-module pickles written by the reference (whose objects only carry the reference's own attributes,
+    models.py:28-29,62-68) evaluate here unchanged, and pickles written here carry nothing the reference lacks."""
+    _ACT_INDEX = 0
+    precision = None          # None = spatial_vae.functional.default_precision(); may be set per instance
+
+    @property
+    def activation_code(self):
+        return SF.activation_code(type(self.layers[self._ACT_INDEX]))
+
+    @property
+    def resid(self):
+        return any(isinstance(m, ResidLinear) for m in self.layers)
+
+
+class InferenceNetwork(_Derived, nn.Module):
     """Encoder MLP: image (B, n) -> (z_mu, z_logstd), each (B, latent_dim) (reference models.py:24-54)."""
+    _ACT_INDEX = 1            # layers = [Linear, act, ...]
 
     def __init__(self, n, latent_dim, hidden_dim, num_layers=1, activation=nn.Tanh, resid=False):
         super().__init__()
         self.latent_dim = latent_dim
         self.n = n
-        self.resid = resid
         self.layers = nn.Sequential(*_stack(n, hidden_dim, num_layers, activation, resid),
                                     nn.Linear(hidden_dim, 2 * latent_dim))
-        self.activation_code = SF.activation_code(activation)
+        SF.activation_code(activation)        # unsupported activations fail at construction
         print(self)
 
     def forward(self, x):
@@ -63,7 +79,7 @@ class InferenceNetwork(nn.Module):
         return out[:, :self.latent_dim], out[:, self.latent_dim:]
 
 
-class SpatialGenerator(nn.Module):
+class SpatialGenerator(_Derived, nn.Module):
     """Coordinate-conditioned decoder, evaluated once per pixel (reference models.py:57-132):
     y[b,p,:] = sigmoid(W_o h_{L-1} + b_o),  h_0 = act(W_c x[b,p] + b_c + W_z z[b]),
     h_l = act(W_l h_{l-1} + b_l)."""
@@ -74,7 +90,6 @@ class SpatialGenerator(nn.Module):
         self.softplus = softplus
         self.expand_coords = expand_coords
         self.latent_dim = latent_dim
-        self.resid = resid
         coord_features = 5 if expand_coords else 2
         self.coord_linear = nn.Linear(coord_features, hidden_dim)
         if latent_dim > 0:
@@ -83,8 +98,7 @@ class SpatialGenerator(nn.Module):
                 self.bilinear = nn.Bilinear(coord_features, latent_dim, hidden_dim, bias=False)
         body = _stack(None, hidden_dim, num_layers, activation, resid)   # starts with the activation
         self.layers = nn.Sequential(*body, nn.Linear(hidden_dim, n_out), nn.Sigmoid())
-        self.activation_code = SF.activation_code(activation)
-        self.precision = None     # None = spatial_vae.functional.default_precision()
+        SF.activation_code(activation)        # unsupported activations fail at construction
         print(self)
 
     def forward(self, x, z):

@@ -269,8 +269,35 @@ def cli_defaults_case(name):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def pickle_case(name, seed, **options):
+    """Whole-module pickles exactly as the reference writes them (torch.save(p_net, path), misc_tools.py:93-99,
+    train_particles.py:530-543) plus what the reference modules return on fixed inputs: the interop fixture for
+    loading reference-trained .sav files into the B200 package."""
+    torch.manual_seed(seed)
+    n, Z, H, Hq = 6, 3, 16, 12
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = ref_models.SpatialGenerator(Z, H, n_out=2, num_layers=3, activation=nn.Tanh, **options)
+        q = ref_models.InferenceNetwork(n * n, Z + 3, Hq, num_layers=3, activation=nn.Tanh,
+                                        resid=options.get("resid", False))
+    p.eval().cpu()
+    q.eval().cpu()
+    torch.save(p, os.path.join(OUT, name + "_generator.sav"))
+    torch.save(q, os.path.join(OUT, name + "_inference.sav"))
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(4, n * n, 2, generator=g) * 2 - 1
+    z = torch.randn(4, Z, generator=g)
+    y = torch.randn(4, n * n, generator=g)
+    with torch.no_grad():
+        y_hat = p(x, z)
+        z_mu, z_logstd = q(y)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x.numpy(), z=z.numpy(), y=y.numpy(), y_hat=y_hat.numpy(),
+                        z_mu=z_mu.numpy(), z_logstd=z_logstd.numpy())
+
+
 if __name__ == "__main__":
     cli_defaults_case("cli_defaults")
+    pickle_case("ref_pickle_plain", 41)
+    pickle_case("ref_pickle_options", 42, softplus=True, resid=True, expand_coords=True, bilinear=True)
     mnist_case("mnist_rt", True, True)
     mnist_case("mnist_r", True, False, seed=11)
     mnist_case("mnist_t", False, True, seed=12)

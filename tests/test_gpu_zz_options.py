@@ -218,3 +218,27 @@ def test_particles_command_line_with_every_option():
     assert len(rows) == 4
     vals = [float(r[-3]) for r in rows]
     assert all(math.isfinite(v) for v in vals) and vals[2] > vals[0]
+
+
+@pytest.mark.parametrize("name", ["ref_pickle_plain", "ref_pickle_options"])
+def test_reference_written_pickles_evaluate_here(name):
+    """Whole-module .sav files written BY THE REFERENCE (tests/golden/ref_pickle_*.sav, produced by
+    tests/golden/make_golden.py with the reference's classes) unpickle into this package's classes and give the
+    reference's outputs: a user's trained models move over without conversion."""
+    import spatial_vae.models as M
+    dev = _cuda()
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(gold, name + ".npz"))
+    p = torch.load(os.path.join(gold, name + "_generator.sav"), weights_only=False)
+    q = torch.load(os.path.join(gold, name + "_inference.sav"), weights_only=False)
+    assert type(p) is M.SpatialGenerator and type(q) is M.InferenceNetwork
+    assert p.resid == q.resid == (name == "ref_pickle_options")
+    p, q = p.to(dev), q.to(dev)
+    p.precision = "parity"
+    t = lambda k: torch.from_numpy(d[k]).to(dev)
+    with torch.no_grad():
+        y_hat = p(t("x"), t("z"))
+        z_mu, z_logstd = q(t("y"))
+    np.testing.assert_allclose(y_hat.cpu().numpy(), d["y_hat"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(z_mu.cpu().numpy(), d["z_mu"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(z_logstd.cpu().numpy(), d["z_logstd"], rtol=1e-5, atol=1e-6)

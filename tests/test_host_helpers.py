@@ -156,3 +156,50 @@ def test_command_line_flags_and_defaults_match_the_reference():
         for k, v in ref[name].items():
             assert mine.get(k) == v, (name, k, v, mine.get(k))
         assert sorted(set(mine) - set(ref[name])) == ["precision", "seed", "synthetic", "synthetic_size", "yes"]
+
+
+def test_pickles_written_here_load_in_the_reference(tmp_path):
+    """The other direction of the .sav interop: whole-module pickles written by this package (driver.save_models)
+    unpickle into the REFERENCE's classes and evaluate there (needs the reference checkout, so it only runs in the
+    build container); outputs are compared with the oracle on the same parameters."""
+    import contextlib
+    import io
+    import os
+    import subprocess
+    import sys
+    import torch
+    ref = os.environ.get("SVAE_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "spatial_vae")):
+        pytest.skip("reference checkout not available")
+    import spatial_vae.models as M
+    from spatial_vae import driver as D
+    from oracle import svae_oracle as O
+    torch.manual_seed(9)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=2, num_layers=3, softplus=True, resid=True, expand_coords=True, bilinear=True)
+        q = M.InferenceNetwork(36, 6, 12, num_layers=3, resid=True)
+    p.precision = "parity"
+    D.save_models(str(tmp_path / "run"), "07", None, p, q, torch.device("cpu"))
+    x, z, y = torch.rand(2, 36, 2) * 2 - 1, torch.randn(2, 3), torch.randn(2, 36)
+    torch.save({"x": x, "z": z, "y": y}, tmp_path / "inputs.pt")
+    code = "\n".join([
+        "import sys, torch",
+        f"sys.path.insert(0, {ref!r})",
+        "import spatial_vae.models as RM",
+        f"p = torch.load({str(tmp_path / 'run_generator_epoch07.sav')!r}, weights_only=False)",
+        f"q = torch.load({str(tmp_path / 'run_inference_epoch07.sav')!r}, weights_only=False)",
+        "assert type(p) is RM.SpatialGenerator and type(q) is RM.InferenceNetwork and not p.training",
+        f"d = torch.load({str(tmp_path / 'inputs.pt')!r})",
+        "with torch.no_grad():",
+        "    out = {'y_hat': p(d['x'], d['z']), 'zq': torch.cat(q(d['y']), 1)}",
+        f"torch.save(out, {str(tmp_path / 'outputs.pt')!r})"])
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = torch.load(tmp_path / "outputs.pt")
+    dec = O.decoder_params_from_state({k: v.detach() for k, v in p.state_dict().items()})
+    enc = O.encoder_params_from_state({k: v.detach() for k, v in q.state_dict().items()})
+    y_ref = O.decoder_forward(dec, x, z, "tanh", softplus=True)
+    mu, ls = O.encoder_forward(enc, y, "tanh", True)
+    assert torch.allclose(out["y_hat"], y_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out["zq"], torch.cat([mu, ls], 1), rtol=1e-5, atol=1e-6)
