@@ -22,8 +22,14 @@ from spatial_vae import driver as D            # noqa: E402
 from spatial_vae.trainer import Trainer        # noqa: E402
 
 eval_minibatch = D.eval_minibatch_galaxy
-minibatch_for_display = D.minibatch_for_display
 random_minibatch_generator = D.random_minibatch_generator
+
+
+def minibatch_for_display(x, y, q_net, p_net, rotate=True, translate=True, z_scale=1, use_cuda=False):
+    """Same signature as the reference's galaxy driver, which takes q_net BEFORE p_net (train_galaxy.py:131), unlike
+    the mnist driver (train_mnist.py:93)."""
+    return D.minibatch_for_display(x, y, p_net, q_net, rotate=rotate, translate=translate, z_scale=z_scale,
+                                   use_cuda=use_cuda)
 
 
 def _both(name):

@@ -182,8 +182,17 @@ def galaxy_case(name, n=4, B=3, Z=4, L=3, seed=3, z_scale=1.0):
         elbo, logp, kl, y_hat = train_galaxy.eval_minibatch(x, y, p, q, rotate=True, translate=True,
                                                            dx_scale=0.1, theta_prior=np.pi, z_scale=z_scale)
     (-elbo).backward()
+    # display / generation helpers (train_galaxy.py:131-183; note the argument order q_net, p_net), with the
+    # normal draws injected: r = eps for the posterior sample, z_rand for the prior sample
+    z_rand = torch.randn(B, Z, generator=g)
+    with torch.no_grad():
+        with inject_eps(eps):
+            display = train_galaxy.minibatch_for_display(x, y, q, p, rotate=True, translate=True, z_scale=0.8)
+        with inject_eps(z_rand):
+            generated = train_galaxy.random_minibatch_generator(x, y, p, Z, z_scale=0.8)
     d = pack(p, q, dict(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, y_hat=y_hat, n=n, L=L,
-                        z_scale=z_scale, theta_prior=np.pi, dx_scale=0.1))
+                        z_scale=z_scale, theta_prior=np.pi, dx_scale=0.1, z_rand=z_rand, display=display,
+                        generated=generated))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 
 

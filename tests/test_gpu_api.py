@@ -26,6 +26,24 @@ def _dev():
     return torch.device("cuda:0")
 
 
+@contextlib.contextmanager
+def _inject_normal(values):
+    """Make the next Tensor.normal_() on a tensor of this shape return `values` (how the fixtures pin the reference's
+    random draws, see tests/golden/make_golden.py)."""
+    orig = torch.Tensor.normal_
+
+    def patched(self, *a, **k):
+        if tuple(self.shape) == tuple(values.shape):
+            return self.copy_(values)
+        return orig(self, *a, **k)
+
+    torch.Tensor.normal_ = patched
+    try:
+        yield
+    finally:
+        torch.Tensor.normal_ = orig
+
+
 def _script(name):
     spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(PKG, name + ".py"))
     mod = importlib.util.module_from_spec(spec)
@@ -145,9 +163,20 @@ def test_train_galaxy_eval_minibatch():
     np.testing.assert_allclose(y_hat.detach().cpu().numpy(), d["y_hat"], atol=1e-6)
     (-elbo).backward()
     _check_module_grads(p, q, d)
-    z = tg.random_minibatch_generator(x, y, p, 4)
-    disp = tg.minibatch_for_display(x, y, q, p) if False else tg.minibatch_for_display(x, y, p, q)
-    assert z.shape == y.shape and disp.shape == y.shape and float(disp.min()) >= 0 and float(disp.max()) <= 1
+    # display / generation helpers against what the reference returned for the same injected normal draws
+    # (train_galaxy.py:131-183; the galaxy driver's minibatch_for_display takes q_net BEFORE p_net)
+    p.precision = "parity"
+    with _inject_normal(torch.from_numpy(d["eps"])):
+        disp = tg.minibatch_for_display(x, y, q, p, rotate=True, translate=True, z_scale=0.8)
+    with _inject_normal(torch.from_numpy(d["z_rand"])):
+        gen = tg.random_minibatch_generator(x, y, p, 4, z_scale=0.8)
+    assert disp.shape == y.shape and gen.shape == y.shape
+    np.testing.assert_allclose(disp.cpu().numpy(), d["display"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gen.cpu().numpy(), d["generated"], rtol=1e-5, atol=1e-6)
+    tm = _script("train_mnist")                  # the mnist driver's order is p_net, q_net (train_mnist.py:93)
+    import inspect
+    assert list(inspect.signature(tm.minibatch_for_display).parameters)[:4] == ["x", "y", "p_net", "q_net"]
+    assert list(inspect.signature(tg.minibatch_for_display).parameters)[:4] == ["x", "y", "q_net", "p_net"]
 
 
 def test_trainer_runs_the_reference_loop_on_flat_buffers():
