@@ -205,6 +205,44 @@ def run_epoch(trainer: Trainer, x_coord, data, *, train: bool, minibatch_size: i
 
 
 # --------------------------------------------------------------------------------------------------
+# the reference's own per-epoch loops (train_epoch / eval_model of the three drivers), for callers that bring their
+# DataLoader and torch optimiser: each minibatch goes through eval_minibatch (the fused step behind autograd),
+# loss.backward(), optim.step(), optim.zero_grad(), and the running means are accumulated as the reference does
+# (train_mnist.py:127-171,174-226; train_particles.py:151-203,206-248; train_galaxy.py:186-231,234-295).
+# The command lines of this build use run_epoch + Trainer instead (flat buffers, fused Adam, CUDA graph).
+# --------------------------------------------------------------------------------------------------
+def epoch_loop(iterator, eval_call, *, train, p_net, q_net, optim=None, epoch=1, num_epochs=1, total=1,
+               first_batch_hook=None):
+    """eval_call(minibatch) -> (elbo, log_p_x_g_z, kl_div, extras); returns (elbo, loss, kl) running means as Python
+    floats, weighted by minibatch size."""
+    p_net.train(train)
+    q_net.train(train)
+    count = 0
+    elbo_accum = loss_accum = kl_accum = 0.0
+    for it, mb in enumerate(iterator):
+        elbo, logp, kl, extras = eval_call(mb)
+        b = mb[0].size(0)
+        if train:
+            (-elbo).backward()
+            optim.step()
+            optim.zero_grad()
+        elbo_v, loss_v, kl_v = elbo.item(), -logp.item(), kl.item()
+        count += b
+        loss_accum += b * (loss_v - loss_accum) / count
+        elbo_accum += b * (elbo_v - elbo_accum) / count
+        kl_accum += b * (kl_v - kl_accum) / count
+        if train:
+            line = '# [{}/{}] training {:.1%}, ELBO={:.5f}, Error={:.5f}, KL={:.5f}'.format(
+                epoch + 1, num_epochs, count / total, elbo_accum, loss_accum, kl_accum)
+            print(line, end='\r', file=sys.stderr)
+        elif it == 0 and first_batch_hook is not None:
+            first_batch_hook(mb, extras)
+    if train:
+        print(' ' * 80, end='\r', file=sys.stderr)
+    return elbo_accum, loss_accum, kl_accum
+
+
+# --------------------------------------------------------------------------------------------------
 # run bookkeeping (reference src/misc_tools.py, src/file_tools.py): thin, behaviour compatible
 # --------------------------------------------------------------------------------------------------
 def activation_from_flag(name, script):

@@ -32,6 +32,36 @@ def minibatch_for_display(x, y, q_net, p_net, rotate=True, translate=True, z_sca
                                    use_cuda=use_cuda)
 
 
+def train_epoch(iterator, x_coord, p_net, q_net, optim, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+                augment_rotation=False, z_scale=1, epoch=1, num_epochs=1, train_images_len=1, use_cuda=False):
+    """The reference's loop over a DataLoader with a torch optimiser (train_galaxy.py:186-231)."""
+    call = lambda mb: eval_minibatch(x_coord, mb[0], p_net, q_net, rotate=rotate, translate=translate,
+                                     dx_scale=dx_scale, theta_prior=theta_prior, augment_rotation=augment_rotation,
+                                     z_scale=z_scale, use_cuda=use_cuda)
+    return D.epoch_loop(iterator, call, train=True, p_net=p_net, q_net=q_net, optim=optim, epoch=epoch,
+                        num_epochs=num_epochs, total=train_images_len)
+
+
+def eval_model(iterator, x_coord, p_net, q_net, z_dim, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+               z_scale=1, use_cuda=False, to_save_image_samples=False, image_dims=None, epoch='0',
+               output_dir='outputs', save_label=''):
+    """train_galaxy.py:234-295: validation means; optionally PNG grids (reconstruction on the unrotated grid, the
+    decoder output, and samples from the prior) of the first minibatch."""
+    call = lambda mb: eval_minibatch(x_coord, mb[0], p_net, q_net, rotate=rotate, translate=translate,
+                                     dx_scale=dx_scale, theta_prior=theta_prior, z_scale=z_scale, use_cuda=use_cuda)
+
+    def dump(mb, y_hat):
+        y = mb[0]
+        y_display = minibatch_for_display(x_coord, y, q_net, p_net, rotate=rotate, translate=translate,
+                                          z_scale=z_scale, use_cuda=use_cuda)
+        y_random = random_minibatch_generator(x_coord, y, p_net, z_dim, z_scale=z_scale, use_cuda=use_cuda)
+        for data, tag in ((y_display, '_dis'), (y_hat.detach(), ''), (y_random, '_rnd')):
+            D.export_batch_as_image(data, '{}/images/{}{}_{}.png'.format(output_dir, epoch, tag, save_label), image_dims)
+
+    return D.epoch_loop(iterator, call, train=False, p_net=p_net, q_net=q_net,
+                        first_batch_hook=dump if (to_save_image_samples and image_dims) else None)
+
+
 def _both(name):
     return ['--' + name, '--' + name.replace('_', '-')] if '_' in name else ['--' + name]
 

@@ -26,6 +26,32 @@ eval_minibatch = D.eval_minibatch_mnist
 minibatch_for_display = D.minibatch_for_display
 
 
+def train_epoch(iterator, x_coord, p_net, q_net, optim, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+                epoch=1, num_epochs=1, N=1, use_cuda=False):
+    """The reference's loop over a DataLoader with a torch optimiser (train_mnist.py:127-171)."""
+    call = lambda mb: eval_minibatch(x_coord, mb[0], p_net, q_net, rotate=rotate, translate=translate,
+                                     dx_scale=dx_scale, theta_prior=theta_prior, use_cuda=use_cuda)
+    return D.epoch_loop(iterator, call, train=True, p_net=p_net, q_net=q_net, optim=optim, epoch=epoch,
+                        num_epochs=num_epochs, total=N)
+
+
+def eval_model(iterator, x_coord, p_net, q_net, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+               use_cuda=False, to_save_image_samples=False, image_dims=None, epoch='0', output_dir='outputs',
+               save_label=''):
+    """train_mnist.py:174-226: validation means; optionally PNG grids of the first minibatch."""
+    call = lambda mb: eval_minibatch(x_coord, mb[0], p_net, q_net, rotate=rotate, translate=translate,
+                                     dx_scale=dx_scale, theta_prior=theta_prior, use_cuda=use_cuda)
+
+    def dump(mb, y_hat):
+        y_display = minibatch_for_display(x_coord, mb[0], p_net, q_net, rotate=rotate, translate=translate,
+                                          use_cuda=use_cuda)
+        D.export_batch_as_image(y_display, '{}/images/{}_dis_{}.png'.format(output_dir, epoch, save_label), image_dims)
+        D.export_batch_as_image(y_hat.detach(), '{}/images/{}_{}.png'.format(output_dir, epoch, save_label), image_dims)
+
+    return D.epoch_loop(iterator, call, train=False, p_net=p_net, q_net=q_net,
+                        first_batch_hook=dump if (to_save_image_samples and image_dims) else None)
+
+
 def _both(name):
     return ['--' + name, '--' + name.replace('_', '-')] if '_' in name else ['--' + name]
 

@@ -24,6 +24,32 @@ from spatial_vae.trainer import Trainer        # noqa: E402
 eval_minibatch = D.eval_minibatch_particles
 
 
+def _unpack(mb):
+    return (mb[0], mb[1]) if len(mb) > 1 else (mb[0], None)
+
+
+def train_epoch(iterator, x_coord, mask, p_net, q_net, optim, rotate=True, translate=True, dx_scale=0.1,
+                theta_prior=np.pi, augment_rotation=False, z_scale=1, epoch=1, num_epochs=1, N=1, use_cuda=False):
+    """The reference's loop over a DataLoader of (y,) or (y, ctf) with a torch optimiser (train_particles.py:151-203)."""
+    def call(mb):
+        y, ctf = _unpack(mb)
+        return eval_minibatch(x_coord, y, mask, ctf, p_net, q_net, rotate=rotate, translate=translate,
+                              dx_scale=dx_scale, theta_prior=theta_prior, augment_rotation=augment_rotation,
+                              z_scale=z_scale, use_cuda=use_cuda) + (None,)
+    return D.epoch_loop(iterator, call, train=True, p_net=p_net, q_net=q_net, optim=optim, epoch=epoch,
+                        num_epochs=num_epochs, total=N)
+
+
+def eval_model(iterator, x_coord, mask, p_net, q_net, rotate=True, translate=True, dx_scale=0.1, theta_prior=np.pi,
+               z_scale=1, use_cuda=False):
+    """train_particles.py:206-248 (no augmentation at evaluation time)."""
+    def call(mb):
+        y, ctf = _unpack(mb)
+        return eval_minibatch(x_coord, y, mask, ctf, p_net, q_net, rotate=rotate, translate=translate,
+                              dx_scale=dx_scale, theta_prior=theta_prior, z_scale=z_scale, use_cuda=use_cuda) + (None,)
+    return D.epoch_loop(iterator, call, train=False, p_net=p_net, q_net=q_net)
+
+
 def _both(name):
     return ['--' + name, '--' + name.replace('-', '_')] if '-' in name else ['--' + name]
 

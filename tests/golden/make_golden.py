@@ -278,6 +278,19 @@ def cli_defaults_case(name):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def driver_signatures_case(name):
+    """inspect.signature of every function the three reference driver scripts define themselves."""
+    import inspect
+    import json
+    out = {}
+    for mod in (train_mnist, train_particles, train_galaxy):
+        for fn, obj in inspect.getmembers(mod, inspect.isfunction):
+            if obj.__module__ == mod.__name__:
+                out[f"{mod.__name__}.{fn}"] = str(inspect.signature(obj))
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def pickle_case(name, seed, **options):
     """Whole-module pickles exactly as the reference writes them (torch.save(p_net, path), misc_tools.py:93-99,
     train_particles.py:530-543) plus what the reference modules return on fixed inputs: the interop fixture for
@@ -305,6 +318,7 @@ def pickle_case(name, seed, **options):
 
 if __name__ == "__main__":
     cli_defaults_case("cli_defaults")
+    driver_signatures_case("driver_signatures")
     pickle_case("ref_pickle_plain", 41)
     pickle_case("ref_pickle_options", 42, softplus=True, resid=True, expand_coords=True, bilinear=True)
     mnist_case("mnist_rt", True, True)

@@ -203,3 +203,27 @@ def test_pickles_written_here_load_in_the_reference(tmp_path):
     mu, ls = O.encoder_forward(enc, y, "tanh", True)
     assert torch.allclose(out["y_hat"], y_ref, rtol=1e-5, atol=1e-6)
     assert torch.allclose(out["zq"], torch.cat([mu, ls], 1), rtol=1e-5, atol=1e-6)
+
+
+def test_driver_functions_keep_the_reference_signatures():
+    """tests/golden/driver_signatures.json: inspect.signature of every function the reference's three driver scripts
+    define (written from the reference in the build container).  The mirrors define the same names; parameter lists
+    are identical or extend the reference's with trailing optional arguments (eps=..., argv=...)."""
+    import importlib.util
+    import inspect
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "driver_signatures.json")))
+    mods = {}
+    for key, sig in sorted(ref.items()):
+        script, fn = key.split(".")
+        if script not in mods:
+            spec = importlib.util.spec_from_file_location("cli_sig_" + script,
+                                                          os.path.join(root, "spatial-vae_b200", script + ".py"))
+            mods[script] = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mods[script])
+        obj = getattr(mods[script], fn, None)
+        assert obj is not None, key
+        mine = str(inspect.signature(obj))
+        assert mine == sig or mine.startswith(sig[:-1]), (key, sig, mine)
