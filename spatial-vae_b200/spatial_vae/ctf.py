@@ -10,10 +10,10 @@ import numpy as np
 CTF_COLUMNS = ['defocus', 'cs', 'voltage', 'apix', 'bfactor', 'ampcont', 'dfdiff', 'dfang']
 
 
-def parse_ctf(path):
-    """Whitespace separated table, one row per particle, 8 columns (reference ctf.py:27-30)."""
+def parse_ctf(f):
+    """Whitespace separated table (path or file object), one row per particle, 8 columns (reference ctf.py:27-30)."""
     import pandas as pd
-    table = pd.read_csv(path, sep=r'\s+', header=None)
+    table = pd.read_csv(f, sep=r'\s+', header=None)
     table.columns = CTF_COLUMNS
     return table
 
@@ -21,6 +21,22 @@ def parse_ctf(path):
 def electron_wavelength(kilovolts):
     v = np.asarray(kilovolts, dtype=np.float64) * 1e3
     return 12.2639 / np.sqrt(v + 0.97845e-6 * v * v)
+
+
+def compute_2d_ctf(freqs, dfu, dfv, dfang, volt, cs, w, bfactor=None):
+    """CTF at the spatial frequencies freqs (K, 2) in 1/Angstrom: defocus dfu / dfv (Angstrom) along / across the
+    astigmatism axis dfang (radians), voltage in kV, spherical aberration cs in mm, amplitude contrast w, optional
+    B-factor envelope (reference ctf.py:7-24)."""
+    freqs = np.asarray(freqs)
+    fx, fy = freqs[:, 0], freqs[:, 1]
+    s2 = fx * fx + fy * fy
+    lam = electron_wavelength(volt)
+    defocus = 0.5 * (dfu + dfv + (dfu - dfv) * np.cos(2 * (np.arctan2(fy, fx) - dfang)))
+    gamma = 2 * np.pi * (-0.5 * defocus * lam * s2 + 0.25 * (cs * 1e7) * lam ** 3 * s2 ** 2)
+    ctf = np.sqrt(1 - w ** 2) * np.sin(gamma) - w * np.cos(gamma)
+    if bfactor is not None:
+        ctf = ctf * np.exp(-bfactor / 4 * s2)
+    return ctf.astype(freqs.dtype)
 
 
 def ctf_filter(ctf_params, n, m, scale=1):

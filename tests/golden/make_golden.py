@@ -291,6 +291,42 @@ def driver_signatures_case(name):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def ingest_case(name):
+    """The reference's host-side ingest helpers on fixed inputs: image.downsample / crop / normalize,
+    ctf.compute_2d_ctf with astigmatism, and MRC files as mrc.write produces them (default header; make_header +
+    extended header, int16 voxels)."""
+    import io as _io
+    import spatial_vae.image as ref_image
+    import spatial_vae.mrc as ref_mrc
+    rng = np.random.default_rng(17)
+    stack = rng.standard_normal((3, 12, 10)).astype(np.float32)
+    out = {"stack": stack,
+           "down_factor2": ref_image.downsample(stack, factor=2),
+           "down_shape_5x7": ref_image.downsample(stack, shape=(5, 7)),
+           "down_2d": ref_image.downsample(stack[0], factor=1.5),
+           "crop8": ref_image.crop(stack, 8),
+           "norm_default": ref_image.normalize(stack),
+           "norm_r3": ref_image.normalize(stack, radius=3)}
+    freqs = np.stack([g.ravel() for g in np.meshgrid(np.fft.fftfreq(9), np.fft.fftfreq(11), indexing="ij")], 1) / 2.5
+    out["freqs"] = freqs
+    out["ctf_astig"] = ref_ctf.compute_2d_ctf(freqs, 21000.0, 18000.0, 0.6, 300.0, 2.7, 0.1, 120.0)
+    out["ctf_no_b"] = ref_ctf.compute_2d_ctf(freqs, 15000.0, 15000.0, 0.0, 200.0, 2.0, 0.07)
+    buf = _io.BytesIO()
+    ref_mrc.write(buf, stack)
+    out["mrc_default"] = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+    vol = rng.integers(-500, 500, size=(2, 4, 6)).astype(np.int16)
+    hdr = ref_mrc.make_header(vol.shape, (6.0, 4.0, 2.0), (90.0, 90.0, 90.0), mz=2, dtype=np.int16, exthd_size=16)
+    buf = _io.BytesIO()
+    ref_mrc.write(buf, vol, header=hdr, extended_header=bytes(range(16)))
+    out["vol_int16"] = vol
+    out["mrc_int16_ext"] = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+    buf = _io.BytesIO()
+    ref_mrc.write(buf, stack[:1], ax=25.0, ay=30.0, az=1.0, alpha=90.0, beta=90.0, gamma=90.0)
+    out["mrc_single_cell"] = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+    out["modes"] = np.array([ref_mrc.get_mode(np.dtype(t)) for t in ("int8", "int16", "float32", "complex64", "uint16")])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def pickle_case(name, seed, **options):
     """Whole-module pickles exactly as the reference writes them (torch.save(p_net, path), misc_tools.py:93-99,
     train_particles.py:530-543) plus what the reference modules return on fixed inputs: the interop fixture for
@@ -319,6 +355,7 @@ def pickle_case(name, seed, **options):
 if __name__ == "__main__":
     cli_defaults_case("cli_defaults")
     driver_signatures_case("driver_signatures")
+    ingest_case("ingest")
     pickle_case("ref_pickle_plain", 41)
     pickle_case("ref_pickle_options", 42, softplus=True, resid=True, expand_coords=True, bilinear=True)
     mnist_case("mnist_rt", True, True)

@@ -227,3 +227,47 @@ def test_driver_functions_keep_the_reference_signatures():
         assert obj is not None, key
         mine = str(inspect.signature(obj))
         assert mine == sig or mine.startswith(sig[:-1]), (key, sig, mine)
+
+
+def test_ingest_helpers_match_the_reference_fixture():
+    """tests/golden/ingest.npz (written by the reference in the build container): Fourier downsampling, crop,
+    background normalisation, the astigmatic 2-D CTF, and MRC files byte for byte (default header; make_header with an
+    extended header and int16 voxels; a single section with cell dimensions), then parsed back."""
+    import io
+    import spatial_vae.ctf as C
+    import spatial_vae.image as I
+    import spatial_vae.mrc as M
+    d = load_case("ingest")
+    stack = d["stack"]
+    for got, key in ((I.downsample(stack, factor=2), "down_factor2"), (I.downsample(stack, shape=(5, 7)), "down_shape_5x7"),
+                     (I.downsample(stack[0], factor=1.5), "down_2d"), (I.normalize(stack), "norm_default"),
+                     (I.normalize(stack, radius=3), "norm_r3")):
+        assert got.dtype == d[key].dtype and got.shape == d[key].shape, key
+        np.testing.assert_allclose(got, d[key], rtol=1e-5, atol=1e-6, err_msg=key)
+    assert np.array_equal(I.crop(stack, 8), d["crop8"])
+    np.testing.assert_allclose(C.compute_2d_ctf(d["freqs"], 21000.0, 18000.0, 0.6, 300.0, 2.7, 0.1, 120.0),
+                               d["ctf_astig"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(C.compute_2d_ctf(d["freqs"], 15000.0, 15000.0, 0.0, 200.0, 2.0, 0.07), d["ctf_no_b"],
+                               rtol=1e-10, atol=1e-12)
+
+    buf = io.BytesIO()
+    M.write(buf, stack)
+    assert buf.getvalue() == d["mrc_default"].tobytes()
+    vol = d["vol_int16"]
+    hdr = M.make_header(vol.shape, (6.0, 4.0, 2.0), (90.0, 90.0, 90.0), mz=2, dtype=np.int16, exthd_size=16)
+    buf = io.BytesIO()
+    M.write(buf, vol, header=hdr, extended_header=bytes(range(16)))
+    assert buf.getvalue() == d["mrc_int16_ext"].tobytes()
+    buf = io.BytesIO()
+    M.write(buf, stack[:1], ax=25.0, ay=30.0, az=1.0, alpha=90.0, beta=90.0, gamma=90.0)
+    assert buf.getvalue() == d["mrc_single_cell"].tobytes()
+
+    arr, h, ext = M.parse(d["mrc_int16_ext"].tobytes())
+    assert np.array_equal(arr, vol) and arr.dtype == np.int16 and ext == bytes(range(16))
+    assert (h.nx, h.ny, h.nz, h.mode, h.mz, h.next, h.mapc, h.mapr, h.maps) == (6, 4, 2, 1, 2, 16, 1, 2, 3)
+    assert (h.xlen, h.ylen, h.zlen, h.amin, h.amax, h.amean, h.rms) == (6.0, 4.0, 2.0, 0.0, -1.0, -2.0, -1.0)
+    arr, h, _ = M.parse(d["mrc_single_cell"].tobytes())
+    assert arr.shape == stack.shape[1:] and np.array_equal(arr, stack[0]) and (h.xlen, h.ylen) == (25.0, 30.0)
+    assert len(M.MRCHeader._fields) == 49 and M.header_struct.size == 1024
+    assert [M.get_mode(np.dtype(t)) for t in ("int8", "int16", "float32", "complex64", "uint16")] == d["modes"].tolist()
+    assert M.get_mode(np.dtype("2h")) == 3 and M.get_mode(np.dtype("3B")) == 16
