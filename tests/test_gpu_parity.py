@@ -442,50 +442,3 @@ def test_particle_configs_at_full_model_size_against_oracle(cfgname, B):
         rel = np.abs(stats[:, 2].numpy() - ref) / np.abs(ref)
         assert rel.max() <= tol, f"{cfgname} {precision}: {rel.max():.2e}"
 
-
-# The tests below were written after round 1's GPU budget was spent: their bodies have passed on the CPU against
-# tests/simt_emu (SVAE_TEST_BACKEND=emu, tests/test_emu_gpu_suite.py) and run last in this file.
-@pytest.mark.parametrize("precision", ["parity", "fast"])
-def test_softplus_output_channel_matches_oracle(precision):
-    """--softplus (models.py:129-130): softplus on output channel 0 AFTER the sigmoid, with and without fit-noise."""
-    for C, seed in ((1, 11), (2, 12)):
-        dec, enc, grid, y, eps = _random_case("particles", 5, 10, 64, 2, 3, 32, C=C, seed=seed)
-        cfg = O.StepConfig(family="particles", theta_prior=math.pi, softplus=True)
-        out, ograds = O.step_grads(cfg, dec, enc, grid, y, eps)
-        stats, _, grads = _run_cuda(cfg, dec, enc, grid, y, eps, precision)
-        ref = (out["logp_i"] - out["kl_i"]).numpy()
-        tol = 2e-5 if precision == "parity" else 1e-3
-        assert (np.abs(stats[:, 2].numpy() - ref) / np.abs(ref)).max() <= tol
-        gtol = 1e-3 if precision == "parity" else 5e-2
-        for i, (g, r) in enumerate(zip(grads, ograds)):
-            scale = float(r.abs().max()) + 1e-8
-            assert float((g - r).abs().max()) <= gtol * scale, f"C={C} grad {i}"
-
-
-@pytest.mark.parametrize("precision", ["parity", "fast"])
-def test_softplus_golden_fixture(precision):
-    """--softplus against the reference-generated fixture (3-layer decoder and encoder)."""
-    from tests.helpers import option_cfg
-    d = load_case("particles_opt_softplus")
-    dec, enc = oracle_params(d)
-    cfg = option_cfg(d)
-    grid, y, eps, kw = _golden_inputs(d)
-    stats, _, grads = _run_cuda(cfg, dec, enc, grid, y, eps, precision)
-    tol = 2e-5 if precision == "parity" else 1e-3
-    assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= tol * abs(float(d["elbo"])) + 1e-5
-    if precision == "parity":
-        for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
-            np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=5e-4, atol=5e-6, err_msg=f"grad {i}")
-
-
-def test_activation_variants_match_oracle():
-    """ReLU and sigmoid hidden activations (train_galaxy.py:426-434) in both precisions."""
-    for act in ("relu", "sigmoid"):
-        dec, enc, grid, y, eps = _random_case("galaxy", 4, 8, 96, 3, 3, 40, C=3, seed=21)
-        cfg = O.StepConfig(family="galaxy", theta_prior=math.pi, activation=act)
-        out, _ = O.step_grads(cfg, dec, enc, grid, y, eps)
-        ref = (out["logp_i"] - out["kl_i"]).numpy()
-        for precision, tol in (("parity", 2e-5), ("fast", 2e-3)):
-            stats, _, _ = _run_cuda(cfg, dec, enc, grid, y, eps, precision)
-            rel = (np.abs(stats[:, 2].numpy() - ref) / np.abs(ref)).max()
-            assert rel <= tol, f"{act} {precision}: {rel:.2e}"
