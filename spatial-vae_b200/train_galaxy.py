@@ -116,26 +116,29 @@ def main(argv=None):
     if args.synthetic > 0:
         side = args.synthetic_size or 64
         g = np.random.default_rng(1234)
-        images = (g.random((args.synthetic, side, side, 3)) * 255).astype(np.uint8)
+        images_train = (g.random((args.synthetic, side, side, 3)) * 255).astype(np.uint8)
+        images_val = (g.random((max(args.synthetic // 4, 1), side, side, 3)) * 255).astype(np.uint8)
     else:
-        images = np.load(args.train_path)
+        # validation runs on the TEST file: this fork commented the --val_split split of the training file out
+        # ("revert back to using test set for validation", reference train_galaxy.py:362-382)
+        images_train = np.load(args.train_path)
+        images_val = np.load(args.test_path)
         if args.make_mono:      # only the training set is converted (reference train_galaxy.py:366-370)
-            images = np.mean(images, axis=3, keepdims=True)
-        np.random.shuffle(images)
+            images_train = np.mean(images_train, axis=3)
+        np.random.shuffle(images_train)
     if args.num_train_images > 0:
-        images = images[:args.num_train_images]
-    # the reference splits the training file into train / validation by --val_split percent
-    n_val = len(images) * args.val_split // 100
-    images_val, images_train = images[:n_val], images[n_val:]
-    if images.ndim == 3:
-        images_train, images_val = images_train[..., None], images_val[..., None]
+        images_train = images_train[:args.num_train_images]
+        images_val = images_val[:args.num_train_images]
+    if images_train.ndim == 3:
+        images_train = images_train[..., None]
     rows, cols, channels = images_train.shape[1:4]
     y_train = torch.from_numpy(np.ascontiguousarray(images_train)).float() / 255
     y_val = torch.from_numpy(np.ascontiguousarray(images_val)).float() / 255
     if args.invert_colours:
         y_train, y_val = 1 - y_train, 1 - y_val
-    y_train = y_train.view(-1, rows * cols, channels).to(device)
-    y_val = y_val.view(-1, rows * cols, channels).to(device)
+    y_train = y_train.reshape(-1, rows * cols, channels).to(device)
+    y_val = y_val.reshape(-1, rows * cols, channels).to(device)       # (the reference views the 3-channel test file
+    #                                                                    with the training set's channel count)
     x_coord = D.make_grid(rows, cols, device)
 
     print('# training with z-dim:', args.z_dim, file=sys.stderr)

@@ -213,7 +213,8 @@ def test_whole_module_pickles_round_trip(tmp_path):
                          "--p-hidden-dim", "64", "--q-hidden-dim", "64", "--fit-noise", "--mask", "--z-delay", "1",
                          "--seed", "0"], 5),
     ("train_galaxy", ["--synthetic", "64", "--synthetic_size", "8", "--num_epochs", "2", "--minibatch_size", "24",
-                      "--p_hidden_dim", "64", "--p_num_layers", "3", "--q_hidden_dim", "128", "-z", "5", "--seed", "0"], 4),
+                      "--p_hidden_dim", "64", "--p_num_layers", "3", "--q_hidden_dim", "128", "-z", "5", "--seed", "0",
+                      "--learning_rate", "0.002"], 4),
 ])
 def test_command_lines_train_on_synthetic_data(script, argv, cols, capsys):
     _dev()
