@@ -13,6 +13,7 @@
  *   svae_adam_step                     optim.step(); optim.zero_grad()      train_mnist.py:149-150 (Adam :389-392)
  *   svae_gather_rows                   DataLoader(TensorDataset, shuffle)   train_mnist.py:334,395-396
  *   svae_rotate_bicubic                PIL Image.rotate(BICUBIC) loop       train_particles.py:28-43, train_galaxy.py:36-54
+ *   svae_ctf_filter                    ctf_filter's per-particle ifft2 loop spatial_vae/ctf.py:33-56
  *   svae_gemm_bf16                     one nn.Linear of SpatialGenerator.layers (models.py:82,126) on
  *                                      tcgen05 tensor cores (building block, exposed for tests)
  *
@@ -197,6 +198,12 @@ int  svae_rotation_matrices(const double* angles_deg, int B, int n_rows, int n_c
                             int32_t* mode);
 int  svae_rotate_bicubic(const float* src, float* dst, const double* inv_affine, const int32_t* mode, int B,
                          int n_rows, int n_cols, int channels, int quantize_u8, void* stream);
+
+/* Real-space CTF kernels on the device, all particles in one launch (reference spatial_vae/ctf.py:33-56, a Python loop
+ * with one numpy ifft2 per particle): params (n_particles, 8) fp64 DEVICE rows in the column order of the CTF table
+ * [defocus um, cs mm, voltage kV, apix A/pixel, bfactor, ampcont %, dfdiff, dfang] (ctf.py:27-30);
+ * out (n_particles, n, m) fp32 = -fftshift(ifft2(CTF)).real, computed in fp64. */
+int  svae_ctf_filter(const double* params, int n_particles, int n, int m, double scale, float* out, void* stream);
 
 /* Measures the SM clock on the device: enqueues a one-thread kernel that spins ~20 us and writes
  * cycles/time in MHz to *out_mhz (device pointer).  Measurement aid for bench.py. */

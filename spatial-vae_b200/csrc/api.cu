@@ -856,6 +856,13 @@ int svae_rotation_matrices(const double* angles_deg, int B, int n_rows, int n_co
     return SVAE_OK;
 }
 
+int svae_ctf_filter(const double* params, int n_particles, int n, int m, double scale, float* out, void* stream) {
+    SVAE_REQUIRE(n_particles >= 0 && n > 0 && m > 0 && scale > 0, SVAE_EINVAL, "bad CTF kernel shape");
+    if (n_particles == 0) return SVAE_OK;
+    SVAE_REQUIRE(params && out, SVAE_EINVAL, "null argument");
+    return ctf_filter(params, n_particles, n, m, scale, out, (cudaStream_t)stream);
+}
+
 int svae_sm_clock_probe(float* out_mhz, void* stream) {
     SVAE_REQUIRE(out_mhz != nullptr, SVAE_EINVAL, "null argument");
     return clock_probe(out_mhz, (cudaStream_t)stream);

@@ -25,7 +25,7 @@ PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST}
 EXPORTS = [
     "svae_version", "svae_last_error", "svae_launch_count", "svae_device_sm_count", "svae_workspace_bytes",
     "svae_encoder_forward", "svae_encoder_backward", "svae_decoder_forward", "svae_decoder_backward",
-    "svae_step", "svae_adam_step", "svae_adam_tick", "svae_adam_step_graph", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_sm_clock_probe", "svae_gemm_bf16",
+    "svae_step", "svae_adam_step", "svae_adam_tick", "svae_adam_step_graph", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_ctf_filter", "svae_sm_clock_probe", "svae_gemm_bf16",
 ]
 
 
@@ -92,6 +92,7 @@ def declare(lib):
     lib.svae_gather_rows.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.svae_rotation_matrices.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.svae_rotate_bicubic.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svae_ctf_filter.argtypes = [vp, i32, i32, i32, C.c_double, vp, vp]
     lib.svae_sm_clock_probe.argtypes = [vp, vp]
     lib.svae_gemm_bf16.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]
     for name in EXPORTS:

@@ -527,6 +527,22 @@ def rotate_bicubic(y: torch.Tensor, n_rows: int, n_cols: int, angles_deg, channe
     return out.view_as(y)
 
 
+def ctf_filter(ctf_params, n: int, m: int, scale: float = 1.0, device=None) -> torch.Tensor:
+    """spatial_vae.ctf.ctf_filter on the device: (N, n, m) fp32 real-space kernels for a parsed CTF table (a pandas
+    frame or anything indexable by the column names), all particles in one launch instead of the reference's Python
+    loop over numpy ifft2 calls (reference ctf.py:33-56)."""
+    import numpy as np
+    from .ctf import CTF_COLUMNS
+    table = np.stack([np.asarray(ctf_params[c], dtype=np.float64) for c in CTF_COLUMNS], axis=1)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    params = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
+    _require_cuda(params)
+    out = torch.empty(params.shape[0], n, m, dtype=torch.float32, device=dev)
+    L.check(L.lib.svae_ctf_filter(_ptr(params), params.shape[0], int(n), int(m), float(scale), _ptr(out), _stream()),
+            "svae_ctf_filter")
+    return out
+
+
 def gemm_bf16(mode: int, A: torch.Tensor, W: torch.Tensor, *, M: int, N: int, K: int, bias=None, aux=None,
               activation: int = L.ACT_TANH, out: torch.Tensor) -> torch.Tensor:
     """Raw access to the tcgen05 GEMM building block (tests)."""

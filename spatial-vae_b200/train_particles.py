@@ -131,15 +131,16 @@ def main(argv=None):
         print('# normalizing particles', file=sys.stderr)
         images_train, images_test = D.normalize_particles(images_train), D.normalize_particles(images_test)
 
-    # CTF kernels are odd-sized: 40x40 images get 39x39 kernels (reference train_particles.py:353-358)
+    # CTF kernels are odd-sized: 40x40 images get 39x39 kernels (reference train_particles.py:353-358); they are built
+    # on the device, all particles in one launch (svae_ctf_filter), not in the reference's per-particle numpy loop
     kn, km = (n - 1 if n % 2 == 0 else n), (m - 1 if m % 2 == 0 else m)
     ctf_train = ctf_test = None
     if args.ctf_train is not None:
         print('# loading CTF filters:', args.ctf_train, file=sys.stderr)
-        ctf_train = torch.from_numpy(C.ctf_filter(C.parse_ctf(args.ctf_train), kn, km, scale=args.scale)).float().to(device)
+        ctf_train = SF.ctf_filter(C.parse_ctf(args.ctf_train), kn, km, scale=args.scale, device=device)
     if args.ctf_test is not None:
         print('# loading CTF filters:', args.ctf_test, file=sys.stderr)
-        ctf_test = torch.from_numpy(C.ctf_filter(C.parse_ctf(args.ctf_test), kn, km, scale=args.scale)).float().to(device)
+        ctf_test = SF.ctf_filter(C.parse_ctf(args.ctf_test), kn, km, scale=args.scale, device=device)
 
     x_coord = D.make_grid(n, m, device)
     y_train = torch.from_numpy(np.ascontiguousarray(images_train)).float().view(-1, n * m).to(device)

@@ -19,7 +19,7 @@ CSRC = os.path.join(ROOT, "spatial-vae_b200", "csrc")
 ASAN = os.environ.get("SVAE_EMU_ASAN") == "1"      # out-of-bounds hunting: run python with LD_PRELOAD=libasan.so
 BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 OUT = os.path.join(BUILD, "libsvae_emu.so")
-SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu"]
+SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu", "ingest_kernels.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
 
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)<<<(.*?)>>>\(")

@@ -125,6 +125,14 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     return r;
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline void sincospi(double x, double* s, double* c) {       // exact at multiples of 1/2 like CUDA's, else libm
+    const double r = x - 2.0 * floor(x / 2.0);               // [0, 2)
+    if (r == 0.0) { *s = 0.0; *c = 1.0; }
+    else if (r == 0.5) { *s = 1.0; *c = 0.0; }
+    else if (r == 1.0) { *s = 0.0; *c = -1.0; }
+    else if (r == 1.5) { *s = -1.0; *c = 0.0; }
+    else { *s = sin(M_PI * r); *c = cos(M_PI * r); }
+}
 inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }
 inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
 inline long long clock64() { return (long long)(svae_emu::globaltimer() * 2); }   // "2 GHz"

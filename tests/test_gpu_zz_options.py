@@ -390,3 +390,29 @@ def test_activation_variants_match_oracle():
             stats, _, _ = _run_parity_suite(cfg, dec, enc, grid, y, eps, precision)
             rel = (np.abs(stats[:, 2].numpy() - ref) / np.abs(ref)).max()
             assert rel <= tol, f"{act} {precision}: {rel:.2e}"
+
+
+def test_device_ctf_filter_matches_the_reference_kernels():
+    """svae_ctf_filter (all particles in one launch, fp64 separable inverse DFT) against the kernels the REFERENCE's
+    ctf_filter produced (tests/golden/ctf_kernels.npz) and against the host rewrite for odd, even and rectangular
+    sizes and a pixel-size scale."""
+    import pandas as pd
+    import spatial_vae.ctf as C
+    import spatial_vae.functional as SF
+    dev = _cuda()
+    d = load_case("ctf_kernels")
+    table = pd.DataFrame({c: d[c] for c in C.CTF_COLUMNS})
+    got = SF.ctf_filter(table, int(d["n"]), int(d["m"]), device=dev).cpu().numpy()
+    assert got.shape == d["kernels"].shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, d["kernels"], rtol=1e-5, atol=1e-8)
+    rng = np.random.default_rng(5)
+    N = 7
+    table = pd.DataFrame(dict(defocus=rng.uniform(0.5, 4, N), cs=rng.uniform(0.01, 2.7, N),
+                              voltage=rng.choice([120.0, 200.0, 300.0], N), apix=rng.uniform(1.0, 3.0, N),
+                              bfactor=rng.uniform(0, 200, N), ampcont=rng.uniform(5, 15, N), dfdiff=np.zeros(N),
+                              dfang=rng.uniform(0, 180, N)))
+    for n, m, scale in ((39, 39, 1.0), (12, 12, 1.0), (9, 14, 2.0), (1, 5, 1.0)):
+        ref = C.ctf_filter(table, n, m, scale=scale)
+        got = SF.ctf_filter(table, n, m, scale=scale, device=dev).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-8, err_msg=f"{n}x{m} scale {scale}")
+    assert SF.ctf_filter(table.iloc[:0], 5, 5, device=dev).shape == (0, 5, 5)
