@@ -14,10 +14,17 @@ DESELECT = "not tc_gemm and not c1_shape and not c2_full_size and not full_model
 
 
 def test_gpu_test_bodies_pass_on_the_simt_emulation():
+    from tests.simt_emu.build import build
+    build()                                 # once, here: the workers below must not compile it concurrently
     env = dict(os.environ, SVAE_TEST_BACKEND="emu")
     env.pop("SVAE_CTF_FAST", None)
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_api.py", "tests/test_gpu_parity.py",
-           "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", DESELECT]
+           "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", DESELECT]
+    try:                                    # four workers when pytest-xdist is available (each loads its own library)
+        import xdist  # noqa: F401
+        cmd += ["-n", "4"]
+    except ImportError:
+        cmd += ["-x"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail
