@@ -111,3 +111,58 @@ def test_random_configuration_matches_oracle(emu, seed):
             for i, (a, b) in enumerate(zip(grads, ograds)):
                 lim = 2e-3 * float(b.abs().max()) + 2e-6
                 assert float((a - b).abs().max()) <= lim, (c, i, float((a - b).abs().max()), lim)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_module_configuration_matches_oracle(emu, seed):
+    """SpatialGenerator / InferenceNetwork as autograd modules (svae_decoder_forward/backward with explicit
+    coordinates, svae_encoder_forward/backward) for random shapes and options, PARITY precision: outputs and the
+    gradients w.r.t. every parameter, x and z against the oracle's autograd."""
+    import contextlib
+    import io
+    import torch.nn as nn
+    import spatial_vae.models as M
+    r = np.random.default_rng(1000 + seed)
+    B, P = int(r.integers(1, 4)), int(r.choice([5, 12, 70]))          # P = 70 spans two 64-row blocks
+    H, L, Z = int(r.choice([7, 16, 33, 64])), int(r.integers(1, 4)), int(r.choice([0, 1, 4]))
+    C = int(r.integers(1, 4))
+    act_name = str(r.choice(["tanh", "leakyrelu", "relu", "sigmoid"]))
+    act = {"tanh": nn.Tanh, "leakyrelu": nn.LeakyReLU, "relu": nn.ReLU, "sigmoid": nn.Sigmoid}[act_name]
+    resid, expand = bool(r.integers(0, 3) == 0), bool(r.integers(0, 2))
+    bilinear = bool(r.integers(0, 2)) and Z > 0
+    softplus = bool(r.integers(0, 2))
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(Z, H, n_out=C, num_layers=L, activation=act, softplus=softplus, resid=resid,
+                               expand_coords=expand, bilinear=bilinear)
+        q = M.InferenceNetwork(P, Z + 2, int(r.choice([6, 20])), num_layers=int(r.integers(1, 4)), activation=act,
+                               resid=resid)
+    p.precision = "parity"
+    dec = O.decoder_params_from_state({k: v.detach().clone() for k, v in p.state_dict().items()})
+    enc = O.encoder_params_from_state({k: v.detach().clone() for k, v in q.state_dict().items()})
+    x, yin = torch.rand(B, P, 2) * 2 - 1, torch.randn(B, P)
+    z = torch.randn(B, Z) if Z > 0 else None
+    w_y, w_q = torch.randn(B, P, C), torch.randn(B, 2 * (Z + 2))
+    xr = x.clone().requires_grad_()
+    zr = z.clone().requires_grad_() if Z > 0 else None
+    leaves = [t.requires_grad_() for t in O.flatten_params(dec, enc)]
+    dec_r, enc_r = O.unflatten_like(dec, enc, leaves)
+    y_ref = O.decoder_forward(dec_r, xr, zr, act_name, softplus=softplus)
+    mu, ls = O.encoder_forward(enc_r, yin, act_name, resid)
+    wrt = leaves + [xr] + ([zr] if Z > 0 else [])
+    ref = torch.autograd.grad((y_ref * w_y).sum() + (torch.cat([mu, ls], 1) * w_q).sum(), wrt)
+
+    xd = x.clone().requires_grad_()
+    zd = z.clone().requires_grad_() if Z > 0 else None
+    y_got = p(xd, zd if Z > 0 else torch.zeros(B, 0))
+    mu_g, ls_g = q(yin)
+    ((y_got * w_y).sum() + (torch.cat([mu_g, ls_g], 1) * w_q).sum()).backward()
+    got = [t.grad for t in list(p.parameters()) + list(q.parameters())] + [xd.grad] + ([zd.grad] if Z > 0 else [])
+    cfg = dict(B=B, P=P, H=H, L=L, Z=Z, C=C, act=act_name, resid=resid, expand=expand, bilinear=bilinear)
+    np.testing.assert_allclose(y_got.detach().numpy(), y_ref.detach().numpy(), rtol=1e-4, atol=1e-5, err_msg=str(cfg))
+    np.testing.assert_allclose(mu_g.detach().numpy(), mu.detach().numpy(), rtol=1e-4, atol=1e-5, err_msg=str(cfg))
+    assert len(got) == len(ref)
+    for i, (g, rr) in enumerate(zip(got, ref)):
+        assert g is not None, (cfg, i)
+        lim = 1e-3 * float(rr.abs().max()) + 2e-6
+        assert float((g - rr).abs().max()) <= lim, (cfg, i, float((g - rr).abs().max()), lim)

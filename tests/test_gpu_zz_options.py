@@ -416,3 +416,45 @@ def test_device_ctf_filter_matches_the_reference_kernels():
         got = SF.ctf_filter(table, n, m, scale=scale, device=dev).cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-8, err_msg=f"{n}x{m} scale {scale}")
     assert SF.ctf_filter(table.iloc[:0], 5, 5, device=dev).shape == (0, 5, 5)
+
+
+# (4) the seeded random configurations of tests/test_emu_fuzz.py, on the real device
+@pytest.mark.parametrize("seed", range(0, 48, 2))
+def test_random_step_configuration_on_the_device(seed):
+    _run_fuzz_step(seed)
+
+
+def _run_fuzz_step(seed):
+    """tests/test_emu_fuzz.py::test_random_configuration_matches_oracle with the tensors on the device."""
+    import spatial_vae.functional as SF
+    from spatial_vae import _lib as L
+    import tests.test_emu_fuzz as F
+    dev = _cuda()
+    c = F._draw(seed)
+    dec, enc, y, eps, kw, I = F._params(c, seed)
+    if I == 0:
+        pytest.skip("no latent at all")
+    grid = O.make_grid(c["n_rows"], c["n_cols"])
+    cfg = O.StepConfig(family=c["family"], rotate=c["rotate"], translate=c["translate"], theta_prior=0.9, dx_scale=0.2,
+                       z_scale=0.7 if c["family"] != "mnist" else 1.0, activation=c["act"], softplus=c["softplus"],
+                       resid=c["resid"])
+    out, ograds = O.step_grads(cfg, dec, enc, grid, y, eps, **kw)
+    ref = (out["logp_i"] - out["kl_i"]).numpy()
+    for precision in ("parity", "fast"):
+        d, e, gd, ge = _dev_params(dec, enc, dev)
+        spec = SF.StepSpec(family=c["family"], rotate=c["rotate"], translate=c["translate"], theta_prior=0.9,
+                           dx_scale=0.2, z_scale=0.7, activation=L.ACT_CODES[c["act"]], softplus=c["softplus"],
+                           precision=precision, chunk_images=c["chunk"], resid=c["resid"])
+        kw_lib = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kw.items()}
+        if "ctf" in kw_lib:
+            kw_lib["ctf"] = kw_lib["ctf"].reshape(c["B"], 5, 5)
+        stats, _, _ = SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge, **kw_lib)
+        torch.cuda.synchronize()
+        got = stats[:, 2].cpu().numpy()
+        tol = 3e-5 if precision == "parity" else 1e-2
+        assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)).max() <= tol, (c, precision, got, ref)
+        if precision == "parity":
+            grads = [g.cpu() for g in gd.flat()] + [t.cpu() for pr in ge for t in pr]
+            for i, (a, b) in enumerate(zip(grads, ograds)):
+                lim = 2e-3 * float(b.abs().max()) + 2e-6
+                assert float((a - b).abs().max()) <= lim, (c, i, float((a - b).abs().max()), lim)
