@@ -291,7 +291,7 @@ def main():
     import spatial_vae.functional as SF
     from spatial_vae import _lib as L
     from spatial_vae.trainer import Trainer
-    from oracle import svae_oracle as O
+    from spatial_vae.driver import make_grid
 
     P = c["n"] * c["n"]
     B = c["B"]
@@ -299,7 +299,7 @@ def main():
     spec = SF.StepSpec(family=c["family"], theta_prior=c["theta_prior"], precision=args.precision,
                        chunk_images=args.chunk)
     trainer = Trainer(p_net, q_net, spec, lr=1e-4)
-    grid = O.make_grid(c["n"], c["n"]).to(device)
+    grid = make_grid(c["n"], c["n"], device)
     n_data = 8 * B
     data = synth_images(c, n_data, device, 1234 + rank)
     ctf_all = None
