@@ -101,9 +101,9 @@ def mnist_case(name, rotate, translate, act=nn.Tanh, L=2, n=6, m=5, B=5, Z=3, se
 
 
 def particles_case(name, fit_noise=False, use_ctf=False, use_mask=False, augment=False, z_scale=1.0,
-                   n=6, B=4, Z=2, seed=2):
+                   n=6, B=4, Z=2, seed=2, rotate=True, translate=True):
     P = n * n
-    I = Z + 3
+    I = Z + int(rotate) + 2 * int(translate)
     C = 2 if fit_noise else 1
     p, q = build(P, Z, I, 16, 2, 12, 2, C, nn.Tanh, seed)
     g = torch.Generator().manual_seed(200 + seed)
@@ -132,12 +132,13 @@ def particles_case(name, fit_noise=False, use_ctf=False, use_mask=False, augment
         extra = dict(theta_offset=offset.astype(np.float32), y_enc=y_rot)
         np.random.seed(7)  # the reference draws the same offsets
     with inject_eps(eps):
-        elbo, logp, kl = train_particles.eval_minibatch(x, y, mask, ctf, p, q, rotate=True, translate=True,
+        elbo, logp, kl = train_particles.eval_minibatch(x, y, mask, ctf, p, q, rotate=rotate, translate=translate,
                                                        dx_scale=0.1, theta_prior=np.pi,
                                                        augment_rotation=augment, z_scale=z_scale)
     (-elbo).backward()
     extra.update(y=y, eps=eps, grid=x, elbo=elbo, logp=logp, kl=kl, n=n, z_scale=z_scale,
-                 fit_noise=int(fit_noise), theta_prior=np.pi, dx_scale=0.1)
+                 fit_noise=int(fit_noise), theta_prior=np.pi, dx_scale=0.1, rotate=int(rotate),
+                 translate=int(translate))
     if ctf is not None:
         extra["ctf"] = ctf
     if mask is not None:
@@ -369,6 +370,8 @@ if __name__ == "__main__":
     particles_case("particles_mask", use_mask=True, seed=23)
     particles_case("particles_augment", augment=True, seed=24)
     particles_case("particles_zscale0", z_scale=0.0, seed=25)
+    particles_case("particles_t_only", rotate=False, fit_noise=True, z_scale=0.6, seed=26)
+    particles_case("particles_r_only", translate=False, use_mask=True, seed=27)
     particles_option_case("particles_opt_resid", 31, resid=True)
     particles_option_case("particles_opt_expand", 32, expand_coords=True)
     particles_option_case("particles_opt_bilinear", 33, bilinear=True)

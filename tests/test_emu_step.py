@@ -15,7 +15,8 @@ from tests.helpers import cfg_of, golden_grads, load_case, option_cfg, oracle_pa
 CASES = [("mnist_rt", "mnist"), ("mnist_r", "mnist"), ("mnist_t", "mnist"), ("mnist_none", "mnist"),
          ("mnist_leaky_L3", "mnist"), ("particles_plain", "particles"), ("particles_fitnoise", "particles"),
          ("particles_ctf", "particles"), ("particles_mask", "particles"), ("particles_augment", "particles"),
-         ("particles_zscale0", "particles"), ("galaxy_rgb", "galaxy")]
+         ("particles_zscale0", "particles"), ("particles_t_only", "particles"), ("particles_r_only", "particles"),
+         ("galaxy_rgb", "galaxy")]
 OPTION_CASES = ["particles_opt_resid", "particles_opt_expand", "particles_opt_bilinear", "particles_opt_softplus",
                 "particles_opt_all"]
 

@@ -28,7 +28,7 @@ from tests.test_gpu_api import _inject_normal, _nets, _script
 
 
 OPTION_CASES = ["particles_opt_resid", "particles_opt_expand", "particles_opt_bilinear", "particles_opt_softplus",
-                "particles_opt_all"]
+                "particles_opt_all", "particles_t_only", "particles_r_only"]   # + the particle driver without theta / dx
 
 
 @pytest.fixture(autouse=True)
@@ -54,7 +54,11 @@ def _dev_params(dec, enc, dev):
     return d, e, gd, ge
 
 
-def _run(cfg, dec, enc, grid, y, eps, precision, chunk=0):
+def _mask(d):
+    return torch.from_numpy(d["mask"]) if "mask" in d else None
+
+
+def _run(cfg, dec, enc, grid, y, eps, precision, chunk=0, mask=None):
     import spatial_vae.functional as SF
     from spatial_vae import _lib as L
     dev = _cuda()
@@ -63,7 +67,7 @@ def _run(cfg, dec, enc, grid, y, eps, precision, chunk=0):
                        theta_prior=cfg.theta_prior, z_scale=cfg.z_scale, activation=L.ACT_CODES[cfg.activation],
                        softplus=cfg.softplus, precision=precision, chunk_images=chunk, resid=cfg.resid)
     stats, y_hat, _ = SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge,
-                                  want_y_hat=True)
+                                  want_y_hat=True, mask=mask.to(dev) if mask is not None else None)
     torch.cuda.synchronize()
     return stats.cpu(), y_hat.cpu(), [g.cpu() for g in gd.flat()] + [t.cpu() for pr in ge for t in pr]
 
@@ -79,7 +83,7 @@ def test_option_step_matches_reference_golden_parity_precision(name):
     dec, enc = oracle_params(d)
     cfg = option_cfg(d)
     grid, y, eps = _inputs(d)
-    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "parity")
+    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "parity", mask=_mask(d))
     for col, key in ((2, "elbo"), (0, "logp"), (1, "kl")):
         np.testing.assert_allclose(float(stats[:, col].mean()), float(d[key]), rtol=2e-5, atol=2e-6, err_msg=key)
     ref = golden_grads(d)
@@ -94,7 +98,7 @@ def test_option_step_matches_reference_golden_fast_precision(name):
     dec, enc = oracle_params(d)
     cfg = option_cfg(d)
     grid, y, eps = _inputs(d)
-    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "fast")
+    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "fast", mask=_mask(d))
     assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= 1e-3 * abs(float(d["elbo"])) + 1e-4
     for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
         scale = float(r.abs().max()) + 1e-6
