@@ -172,3 +172,25 @@ def test_rotation_matrices_match_pillow_recipe(built):
         expect_mode = {0.0: 1, 180.0: 2, 90.0: 3, 270.0: 4}.get(a, 0)
         assert modes[b] == expect_mode
         assert mats[b].tolist() == rotate_matrix(ang[b], 40, 40), (ang[b], mats[b], rotate_matrix(ang[b], 40, 40))
+
+
+def test_product_sources_keep_to_the_rules():
+    """Static guards: the product never imports the oracle or the test emulator, never names the batched-memcpy runtime
+    entry points this environment forbids, and the library sources contain no CPU fallback switch."""
+    import glob
+    banned_api = ["cudaMemcpy" + "BatchAsync", "cudaMemcpy3D" + "BatchAsync", "cuMemcpy" + "BatchAsync",
+                  "cuMemcpy3D" + "BatchAsync"]
+    product = glob.glob(os.path.join(ROOT, "spatial-vae_b200", "**", "*.py"), recursive=True) + \
+        glob.glob(os.path.join(ROOT, "spatial-vae_b200", "csrc", "*.cu*")) + [os.path.join(ROOT, "include", "svae_b200.h")]
+    assert len(product) > 15
+    for path in product:
+        text = open(path).read()
+        for name in banned_api:
+            assert name not in text, (path, name)
+        if path.endswith(".py"):
+            assert "import oracle" not in text and "from oracle" not in text, path
+            assert "simt_emu" not in text and "emu_backend" not in text, path
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    main_src = bench[bench.index("def main():"):]
+    assert "oracle" not in main_src.split("cpu_reference_steps(c, sb")[0].replace("oracle port", ""), \
+        "the measured arm of bench.py must not touch oracle/"
