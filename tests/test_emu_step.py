@@ -232,3 +232,49 @@ def test_emulated_trainer_trajectory(emu, name):
     dec_o, enc_o, _ = O.train_steps(cfg, dec, enc, grid, [y] * 10, eps_seq, lr=1e-3)
     for t, r in zip(list(p.parameters()) + list(q.parameters()), O.flatten_params(dec_o, enc_o)):
         np.testing.assert_allclose(t.detach().numpy(), r.numpy(), rtol=0, atol=1e-4)
+
+
+def test_integration_md_ctypes_stub_works_as_written(emu):
+    """The binding INTEGRATION.md tells a reference maintainer to add is executed as printed (only the library path
+    is redirected to the host build): one svae_step through raw ctypes on a reference-shaped module pair, per-image
+    ELBO against the golden fixture."""
+    import os
+    import re
+    import contextlib
+    import io
+    import spatial_vae.models as M
+    from tests.simt_emu.build import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# spatial_vae/_b200\.py.*?)```", text, flags=re.S).group(1)
+    assert 'C.CDLL("libsvae_b200.so")' in code
+    code = code.replace('C.CDLL("libsvae_b200.so")', f"C.CDLL({build()!r})")
+    code = code.replace("torch.cuda.current_stream().cuda_stream", "0")          # no CUDA stream on the host build
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+
+    d = load_case("mnist_rt")
+    ps = {k[2:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("p.")}
+    qs = {k[2:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("q.")}
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(ps["latent_linear.weight"].shape[1], ps["coord_linear.weight"].shape[0], num_layers=2)
+        q = M.InferenceNetwork(qs["layers.0.weight"].shape[1], qs["layers.4.weight"].shape[0] // 2,
+                               qs["layers.0.weight"].shape[0], num_layers=2)
+    p.load_state_dict(ps)
+    q.load_state_dict(qs)
+    dec_params = [t for t in p.parameters()]
+    gdec, genc = ns["Dec"](), ns["Enc"]()
+    grads = [torch.zeros_like(t) for t in list(p.parameters()) + list(q.parameters())]
+    gdec.coord_w, gdec.coord_b, gdec.latent_w = (g.data_ptr() for g in grads[:3])
+    gdec.hidden_w[0], gdec.hidden_b[0] = grads[3].data_ptr(), grads[4].data_ptr()
+    gdec.out_w, gdec.out_b = grads[5].data_ptr(), grads[6].data_ptr()
+    for i in range(3):
+        genc.w[i], genc.b[i] = grads[7 + 2 * i].data_ptr(), grads[8 + 2 * i].data_ptr()
+    stats = ns["step"](p, q, torch.from_numpy(d["grid"]), torch.from_numpy(d["y"]), torch.from_numpy(d["eps"]),
+                       (gdec, genc), rotate=True, translate=True, theta_prior=float(d["theta_prior"]),
+                       dx_scale=float(d["dx_scale"]))
+    np.testing.assert_allclose(float(stats[:, 2].mean()), float(d["elbo"]), rtol=1e-3)
+    ref = golden_grads(d)
+    for i, (g, r) in enumerate(zip(grads, ref)):
+        assert float((g - r).abs().max()) <= 3e-2 * (float(r.abs().max()) + 1e-6), i
+    assert len(dec_params) == 7
