@@ -17,14 +17,32 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "spatial-vae_b200", "csrc")
 ASAN = os.environ.get("SVAE_EMU_ASAN") == "1"      # out-of-bounds hunting: run python with LD_PRELOAD=libasan.so
-BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
+BUILD = os.path.join(HERE, ("_build_asan" if ASAN else "_build") + ("" if os.environ.get("SVAE_EMU_TC", "kernel") != "ref" else "_ref"))
 OUT = os.path.join(BUILD, "libsvae_emu.so")
 SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu", "ingest_kernels.cu"]
+# SVAE_EMU_TC=kernel (default): tc_gemm.cu itself runs on the host model of tcgen05 / TMA / mbarriers (tc_emu.h);
+# SVAE_EMU_TC=ref: the plain-loop stand-in tc_gemm_ref.cpp (much faster, exercises only the call sequence)
+TC_KERNEL = os.environ.get("SVAE_EMU_TC", "kernel") != "ref"
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
 
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)<<<(.*?)>>>\(")
 DYN_SMEM = re.compile(r"extern __shared__ (?:__align__\(\d+\) )?(\w+) (\w+)\[\];")
 TIMER = re.compile(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)\);')
+
+
+RED_V4 = re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::"l"\((.*?)\), "f"\((.*?)\), "f"\((.*?)\),\s*"f"\((.*?)\), "f"\((.*?)\) : "memory"\);', re.S)
+
+
+def rewrite_tc(text: str) -> str:
+    """tc_gemm.cu: the PTX-wrapper section is replaced by the host model, the one inline red.global.add by atomics."""
+    a = text.index("// ---- PTX wrappers")
+    b = text.index("// ---- descriptors")
+    text = text[:a] + "}  // namespace\n}  // namespace svae\n#include \"tc_emu.h\"\nnamespace svae {\nnamespace {\n" + text[b:]
+    text, n = RED_V4.subn(lambda m: "{ float* red_p = %s; atomicAdd(red_p, %s); atomicAdd(red_p + 1, %s); "
+                                    "atomicAdd(red_p + 2, %s); atomicAdd(red_p + 3, %s); }" % m.groups(), text)
+    if n != 1:
+        raise RuntimeError("simt_emu/build.py: expected exactly one red.global.add.v4.f32 statement in tc_gemm.cu")
+    return text
 
 
 def rewrite(text: str) -> str:
@@ -46,8 +64,9 @@ def newest(paths):
 
 def build(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + \
-             [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc_gemm_ref.cpp", "build.py")] + \
+    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["tc_gemm.cu"]] + \
+             [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc_gemm_ref.cpp", "tc_emu.h", "build.py",
+                                              "include/cuda.h")] + \
              [os.path.join(ROOT, "include", "svae_b200.h")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest(inputs):
         return OUT
@@ -60,7 +79,14 @@ def build(force: bool = False) -> str:
         with open(os.path.join(CSRC, f)) as src, open(out, "w") as dst:
             dst.write(rewrite(src.read()))
         units.append(out)
-    units += [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(HERE, "tc_gemm_ref.cpp")]
+    units.append(os.path.join(HERE, "cuda_emu.cpp"))
+    if TC_KERNEL:
+        out = os.path.join(BUILD, "tc_gemm.cpp")
+        with open(os.path.join(CSRC, "tc_gemm.cu")) as src, open(out, "w") as dst:
+            dst.write(rewrite(rewrite_tc(src.read())))
+        units.append(out)
+    else:
+        units.append(os.path.join(HERE, "tc_gemm_ref.cpp"))
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
              "-I", os.path.join(HERE, "include"), "-I", BUILD, "-I", HERE]
     link = []

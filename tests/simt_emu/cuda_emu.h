@@ -89,22 +89,36 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { ret
 // ---- built-in variables and the fiber scheduler ------------------------------------------------------
 namespace svae_emu {
 
+// wait reasons of a fiber
+enum { RUNNABLE, WAIT_BLOCK, WAIT_WARP, WAIT_NAMED, WAIT_CLUSTER, WAIT_COND, DONE };
+
 struct State {
-    enum { RUNNABLE, WAIT_BLOCK, WAIT_WARP, DONE };
     ucontext_t sched;
     std::vector<ucontext_t> ctx;
     std::vector<int> status;
+    std::vector<int> named_id;        // WAIT_NAMED: barrier id
+    std::vector<int> named_count;     // WAIT_NAMED: participants
+    std::vector<std::function<bool()>> cond;   // WAIT_COND: runnable again once this returns true
+    std::vector<const char*> why;     // WAIT_COND: what the fiber waits for (deadlock report)
     std::vector<char*> stacks;
     std::vector<float> shfl;          // one exchange slot per thread
     std::function<void()>* body = nullptr;
-    int n = 0, cur = 0;
-    void* dyn = nullptr;
+    int n = 0;                        // fibers of the running cluster = cluster_size * threads_per_cta
+    int per_cta = 0, cluster = 1;     // threads per CTA, CTAs per cluster
+    int cur = 0;                      // running fiber
+    unsigned first_block = 0;         // blockIdx.x of CTA 0 of the running cluster
+    std::vector<void*> dyn;           // dynamic shared memory arena of each CTA of the cluster
     size_t dyn_cap = 0;
+    int cta() const { return cur / per_cta; }
+    int tid() const { return cur % per_cta; }
 };
 State& state();
 void yield(int why);
-void run_block(std::function<void()>& body, int nthreads);
-void* dyn_smem();
+void wait_named(int id, int count);
+void wait_until(std::function<bool()> cond, const char* why);
+void run_cluster(std::function<void()>& body, int threads_per_cta, int cluster_size, unsigned first_block, size_t smem);
+void* dyn_smem();                     // arena of the running fiber's CTA
+void* dyn_smem_of(int cta_rank);      // arena of another CTA of the cluster
 unsigned long long globaltimer();
 
 }  // namespace svae_emu
@@ -112,19 +126,24 @@ unsigned long long globaltimer();
 extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 
-inline void __syncthreads() { svae_emu::yield(svae_emu::State::WAIT_BLOCK); }
-inline void __syncwarp(unsigned = 0xffffffffu) { svae_emu::yield(svae_emu::State::WAIT_WARP); }
+inline void __syncthreads() { svae_emu::yield(svae_emu::WAIT_BLOCK); }
+inline void __syncwarp(unsigned = 0xffffffffu) { svae_emu::yield(svae_emu::WAIT_WARP); }
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     svae_emu::State& s = svae_emu::state();
     const int me = s.cur;
     s.shfl[me] = v;
-    svae_emu::yield(svae_emu::State::WAIT_WARP);
+    svae_emu::yield(svae_emu::WAIT_WARP);
     const int partner = (me & ~31) | ((me & 31) ^ lane_mask);
     const float r = (partner < s.n) ? s.shfl[partner] : v;
-    svae_emu::yield(svae_emu::State::WAIT_WARP);
+    svae_emu::yield(svae_emu::WAIT_WARP);
     return r;
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __expf(float x) { return expf(x); }
+inline void __trap() { fprintf(stderr, "svae_emu: __trap()\n"); abort(); }
 inline void sincospi(double x, double* s, double* c) {       // exact at multiples of 1/2 like CUDA's, else libm
     const double r = x - 2.0 * floor(x / 2.0);               // [0, 2)
     if (r == 0.0) { *s = 0.0; *c = 1.0; }
@@ -161,23 +180,19 @@ namespace svae_emu {
 struct Launcher {
     dim3 g, b;
     size_t smem;
-    Launcher(dim3 g_, dim3 b_, size_t smem_ = 0, cudaStream_t = nullptr) : g(g_), b(b_), smem(smem_) {}
+    unsigned cluster;
+    Launcher(dim3 g_, dim3 b_, size_t smem_ = 0, cudaStream_t = nullptr, unsigned cluster_ = 1)
+        : g(g_), b(b_), smem(smem_), cluster(cluster_) {}
     template <typename... P, typename... A>
     void run(void (*k)(P...), A&&... a) {
-        State& s = state();
-        if (smem > s.dyn_cap) {
-            free(s.dyn);
-            s.dyn = aligned_alloc(128, (smem + 127) / 128 * 128);
-            s.dyn_cap = smem;
-        }
         std::function<void()> body = [&]() { k(a...); };
         gridDim = g;
         blockDim = b;
         for (unsigned z = 0; z < g.z; ++z)
             for (unsigned y = 0; y < g.y; ++y)
-                for (unsigned x = 0; x < g.x; ++x) {
+                for (unsigned x = 0; x < g.x; x += cluster) {
                     blockIdx = uint3{x, y, z};
-                    run_block(body, (int)(b.x * b.y * b.z));
+                    run_cluster(body, (int)(b.x * b.y * b.z), (int)cluster, x, smem);
                 }
     }
 };

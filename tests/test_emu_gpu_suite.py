@@ -1,6 +1,6 @@
 """Runs the bodies of the `-m gpu` tests on the CPU against tests/simt_emu (SVAE_TEST_BACKEND=emu, see
 tests/conftest.py): the very tests the B200 box executes at round end, minus the ones that are too large for a
-fiber-based emulation or that need real CUDA machinery (tcgen05 GEMM unit tests, CUDA graphs, full-size shapes).
+fiber-based emulation or that need real CUDA machinery (CUDA graphs, full-size shapes).
 One subprocess, so the emulation patches never leak into the other CPU tests."""
 import os
 import subprocess
@@ -8,9 +8,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# too large for the emulation (minutes) or meaningless on it (they unit-test the tcgen05 kernel, which the
-# emulation replaces by a plain-loop stand-in; CUDA graphs do not exist on a host)
-DESELECT = "not tc_gemm and not c1_shape and not c2_full_size and not full_model_size and not graphed_step"
+# too large for the emulation (minutes), or CUDA graphs (they do not exist on a host).  The tcgen05 GEMM unit tests DO
+# run: tc_gemm.cu itself executes on the host model of tcgen05 / TMA / mbarriers (tests/simt_emu/tc_emu.h).
+DESELECT = "not c1_shape and not c2_full_size and not full_model_size and not graphed_step"
 
 
 def test_gpu_test_bodies_pass_on_the_simt_emulation():
