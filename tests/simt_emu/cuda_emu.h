@@ -83,7 +83,13 @@ inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+// SM count of the emulated device: 148 like a B200, or SVAE_EMU_SMS (a small value makes persistent kernels walk
+// several tiles per CTA, which is where accumulator double-buffering and barrier phases get exercised)
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {
+    const char* e = getenv("SVAE_EMU_SMS");
+    *v = (e != nullptr && atoi(e) > 0) ? atoi(e) : 148;
+    return cudaSuccess;
+}
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 // ---- built-in variables and the fiber scheduler ------------------------------------------------------

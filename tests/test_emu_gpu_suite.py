@@ -29,3 +29,23 @@ def test_gpu_test_bodies_pass_on_the_simt_emulation():
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail
     assert " passed" in tail and " failed" not in tail and " skipped" not in tail, tail
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("sms,cta_group", [("4", "2"), ("3", "1")])
+def test_tcgen05_gemm_persistent_paths_on_a_small_emulated_device(sms, cta_group):
+    """The tcgen05 GEMM unit tests again on an emulated device with only a few SMs, so that every persistent CTA
+    (pair) walks several tiles: accumulator double buffering, ring wrap-around and mbarrier phase flips are exercised
+    (a wrong arrival count or a missing phase flip deadlocks here and the scheduler aborts with the waiters listed).
+    cta_group 2 = CTA pairs (the default), 1 = the single-CTA variant (SVAE_TC_CTA_GROUP=1)."""
+    from tests.simt_emu.build import build
+    build()
+    env = dict(os.environ, SVAE_TEST_BACKEND="emu", SVAE_EMU_SMS=sms, SVAE_TC_CTA_GROUP=cta_group)
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+           "-k", "tc_gemm and not 78400"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and " failed" not in r.stdout, tail
