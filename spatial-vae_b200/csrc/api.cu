@@ -40,10 +40,11 @@ struct Plan {
     size_t xs_k, gs_r, as_r, ws_k[SVAE_MAX_LAYERS], ws_r[SVAE_MAX_LAYERS];
     // decoder options (models.py:65-67,74-75): F coordinate features, K1 per-image moment rows in S,
     // opt = first layer runs through option_kernels.cu; weff (B, H*F) per-image coordinate weights (bilinear),
-    // dlat (B,3) = (d theta, d t0, d t1)
+    // dlat (B,3) = (d theta, d t0, d t1); enc_wres (Hq,Hq) fp32 W + I for the encoder (resid on tensor cores)
     int F = 2, K1 = 3;
     bool opt = false;
-    size_t weff = 0, dlat = 0;
+    size_t weff = 0, dlat = 0, enc_wres = 0;
+    bool resid_tc = false;          // ResidLinear layers on the tensor-core GEMMs: wbf16 also holds the W + I copies
     long w_img_stride = 0;
 };
 
@@ -83,7 +84,17 @@ static int validate(const SvaeShape& s, const SvaeConfig& c) {
 // in the FFMA GEMM epilogue exactly.  Folding it into the bf16 operand (W + I) rounds the diagonal to 2^-8 and was
 // measured (CPU emulation, H = 500, L = 3) at 3e-3..9e-3 relative per-image ELBO error, outside the 1e-3 gate; a
 // tcgen05 epilogue that adds the layer input tile is the next step for this option.
-static bool use_fast(const SvaeConfig& c) { return c.precision == SVAE_PRECISION_FAST && !c.resid; }
+//
+// SVAE_RESID_TC=1 selects the tensor-core route for them instead (written with the tcgen05 host model of
+// tests/simt_emu, not yet run on a GPU): the forward GEMM adds the layer input tile exactly in its epilogue
+// (tc_gemm RES), the dX GEMM sees a bf16 copy of W + I, the encoder's 3-term GEMMs an fp32 copy of W + I.
+static bool resid_on_tensor_cores() {
+    static const bool on = (getenv("SVAE_RESID_TC") != nullptr && getenv("SVAE_RESID_TC")[0] == '1');
+    return on;
+}
+static bool use_fast(const SvaeConfig& c) {
+    return c.precision == SVAE_PRECISION_FAST && (!c.resid || resid_on_tensor_cores());
+}
 
 static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     const bool fast = use_fast(c);
@@ -129,6 +140,8 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.S = take(cur, B * p.K1 * p.Hp * 4);
     p.weff = take(cur, c.bilinear ? B * (size_t)s.H * p.F * 4 : 0);
     p.dlat = take(cur, B * 3 * 4);
+    p.resid_tc = fast && c.resid;
+    p.enc_wres = take(cur, (p.resid_tc && s.Lq > 1) ? (size_t)s.Hq * s.Hq * 4 : 0);
     p.dz = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
     p.g_zo = take(cur, B * 2 * I * 4);
     p.o = take(cur, rows * s.C * 4);
@@ -138,7 +151,8 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.delta_stride = p.act_stride;
     p.delta = take(cur, p.delta_stride * 2);
     p.w_stride = (size_t)p.Hp * p.Hp * 2;
-    p.wbf16 = take(cur, fast ? p.w_stride * (s.L > 1 ? s.L - 1 : 1) : 0);
+    // bf16 hidden weights; with resid_tc a second set with the identity added follows (operands of the dX GEMMs)
+    p.wbf16 = take(cur, fast ? p.w_stride * (s.L > 1 ? s.L - 1 : 1) * (p.resid_tc ? 2 : 1) : 0);
     p.total = cur;
     return SVAE_OK;
 }
@@ -186,6 +200,16 @@ static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderPa
 // built from hi/lo splits of both operands (split3), fp32 accumulate, fp32 output.
 struct EncTc {
     const SvaeShape* s; const Plan* p; char* ws; cudaStream_t st;
+    // weight of hidden layer l as the GEMMs see it: W_l, or an fp32 copy of W_l + I for a ResidLinear layer (l >= 1)
+    int weight(const SvaeEncoderParams& q, int l, const float** w) const {
+        *w = q.w[l];
+        if (p->resid_tc && l > 0) {
+            float* tmp = reinterpret_cast<float*>(ws + p->enc_wres);
+            SVAE_TRY(copy_add_identity(q.w[l], s->Hq, tmp, st));
+            *w = tmp;
+        }
+        return SVAE_OK;
+    }
     int Hqp() const { return p->enc_ld; }
     int kin(int l) const { return l == 0 ? s->P * s->Cin : s->Hq; }
     int kinp(int l) const { return l == 0 ? (int)round_up((long)s->P * s->Cin, 64) : p->enc_ld; }
@@ -200,7 +224,9 @@ static int encoder_forward_tc(const EncTc& e, int act, const SvaeEncoderParams& 
     for (int l = 0; l < s.Lq; ++l) {
         const int k = e.kin(l), kp = e.kinp(l);
         SVAE_TRY(split3(cur, s.B, k, ld, e.b16(e.p->xs_k), s.B, kp, 1, 0, e.st));
-        SVAE_TRY(split3(q.w[l], s.Hq, k, k, e.b16(e.p->ws_k[l]), e.Hqp(), kp, 1, 1, e.st));
+        const float* wl = nullptr;
+        SVAE_TRY(e.weight(q, l, &wl));
+        SVAE_TRY(split3(wl, s.Hq, k, k, e.b16(e.p->ws_k[l]), e.Hqp(), kp, 1, 1, e.st));
         TcExtra f32out;
         f32out.out_f32 = 1;
         SVAE_TRY(tc_gemm(0, s.B, e.Hqp(), 3 * kp, e.b16(e.p->xs_k), 3 * kp, e.b16(e.p->ws_k[l]), 3 * kp, q.b[l], s.Hq,
@@ -249,7 +275,9 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
         if (l == 0) break;
         // g_in (B, Hq) = (g W_l) .* act'(a_in)
         SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->xs_k), s.B, Hqp, 1, 0, e.st));
-        SVAE_TRY(split3(q.w[l], s.Hq, k_in, k_in, e.b16(e.p->ws_r[l]), Hqp, kinp, 0, 1, e.st));
+        const float* wl = nullptr;
+        SVAE_TRY(e.weight(q, l, &wl));
+        SVAE_TRY(split3(wl, s.Hq, k_in, k_in, e.b16(e.p->ws_r[l]), Hqp, kinp, 0, 1, e.st));
         cur ^= 1;
         TcExtra f32out;
         f32out.out_f32 = 1;
@@ -309,6 +337,8 @@ struct DecoderCtx {
     T* delta(int i) const { return reinterpret_cast<T*>(ws + p->delta + p->delta_stride * i); }
     float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
     __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
+    // operand of the dX GEMM of hidden layer l+1: W, or the W + I copy for ResidLinear layers on tensor cores
+    __nv_bfloat16* wbf_dx(int l) const { return wbf(p->resid_tc ? (s->L - 1) + l : l); }
     // first-layer coordinate weights of image 0: W_eff (B, H*F) with bilinear, else coord_linear.weight
     const float* l0_w(const SvaeDecoderParams& dp) const { return c->bilinear ? f(p->weff) : dp.coord_w; }
 };
@@ -335,6 +365,7 @@ int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Svae
     if (fuse_out) SVAE_TRY(fill_rows(d.f(d.p->o), dp.out_b, rows, d.s->C, d.s->C, d.st));
     TcExtra ex;
     if (fuse_out) { ex.out_w = dp.out_w; ex.out_w_ld = d.s->H; ex.dot_c = d.s->C; ex.o_accum = d.f(d.p->o); }
+    if (d.p->resid_tc) { ex.resid = d.act(l - 1); ex.ld_resid = Hp; }      // act(W h + b + h), h added in the epilogue
     return tc_gemm(0, rows, Hp, Hp, d.act(l - 1), Hp, d.wbf(l - 1), Hp, dp.hidden_b[l - 1], d.s->H, nullptr, 0,
                    d.c->activation, d.act(l), Hp, d.st, ex);
 }
@@ -378,7 +409,7 @@ int hidden_backward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Sva
     SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
     TcExtra ex;
     if (red.S != nullptr) { ex.red_S = red.S; ex.red_ld = Hp; ex.red_grid = red.grid; ex.red_P = d.s->P; ex.red_b0 = red.b0; }
-    return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
+    return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf_dx(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
                    delta_prev, Hp, d.st, ex);
 }
 
@@ -399,7 +430,7 @@ static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams
         SVAE_TRY(layer0_forward<T>(s, d.c->activation, b0, nb, dp.coord_w, d.f(d.p->hz), grid, d.f(d.p->img),
                                    x_explicit, s.H, Hp, d.act(0), d.st));
     // FAST precision: the output-layer dot product rides in the epilogue of the last hidden GEMM
-    const bool fuse_out = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3;
+    const bool fuse_out = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3 && !d.p->resid_tc;
     for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows, fuse_out && l == s.L - 1));
     float* yh = y_hat ? y_hat + (size_t)b0 * s.P * s.C : nullptr;
     if (fuse_out) return yh ? logits_to_yhat(d.f(d.p->o), yh, (long)rows * s.C, s.C, d.c->softplus, d.st) : SVAE_OK;
@@ -447,8 +478,13 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
 static int prepare_bf16_weights(const SvaeShape& s, const Plan& p, const SvaeDecoderParams& dp, char* ws,
                                 cudaStream_t st) {
     for (int l = 0; l < s.L - 1; ++l) {
-        SVAE_TRY(to_bf16_padded(dp.hidden_w[l], s.H, s.H,
-                                reinterpret_cast<__nv_bfloat16*>(ws + p.wbf16 + p.w_stride * l), p.Hp, p.Hp, st));
+        __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(ws + p.wbf16 + p.w_stride * l);
+        SVAE_TRY(to_bf16_padded(dp.hidden_w[l], s.H, s.H, w, p.Hp, p.Hp, st));
+        if (p.resid_tc) {      // second copy with the identity added: the dX operand of a ResidLinear layer
+            __nv_bfloat16* wi = reinterpret_cast<__nv_bfloat16*>(ws + p.wbf16 + p.w_stride * ((s.L - 1) + l));
+            SVAE_TRY(to_bf16_padded(dp.hidden_w[l], s.H, s.H, wi, p.Hp, p.Hp, st));
+            SVAE_TRY(add_identity_bf16(dp.hidden_w[l], s.H, wi, p.Hp, st));
+        }
     }
     return SVAE_OK;
 }

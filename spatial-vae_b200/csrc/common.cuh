@@ -106,6 +106,8 @@ struct TcExtra {
     const float* out_w = nullptr; int out_w_ld = 0; int dot_c = 0; float* o_accum = nullptr;
     // modes 0/1: fp32 output (and fp32 aux) instead of bf16
     int out_f32 = 0;
+    // mode 0: ResidLinear (models.py:13-21): out = act(A W^T + bias + resid), resid (M x N, bf16, ld elements)
+    const void* resid = nullptr; int ld_resid = 0;
     // mode 1: per-image moments S[b0 + m/P, {1,x,y}, n] += out[m,n] * {1, grid[m%P]} instead of storing out
     float* red_S = nullptr; int red_ld = 0; const float* red_grid = nullptr; int red_P = 0; int red_b0 = 0;
 };

@@ -98,6 +98,10 @@ int to_bf16_padded(const float* src, int rows, int cols, __nv_bfloat16* dst, int
 int rotate_bicubic(const float* src, float* dst, const double* mat, const int* mode, int B, int h, int w, int C,
                    int quantize_u8, cudaStream_t st);
 
+// ResidLinear helpers of the tensor-core path: dst[i,i] = bf16(src[i,i] + 1) on a converted weight; fp32 W + I
+int add_identity_bf16(const float* src, int n, __nv_bfloat16* dst, int ld, cudaStream_t st);
+int copy_add_identity(const float* src, int n, float* dst, cudaStream_t st);
+
 // per-particle real-space CTF kernels (ingest_kernels.cu): params (N, 8) fp64 device rows
 // [defocus um, cs mm, voltage kV, apix, bfactor, ampcont %, dfdiff, dfang] -> out (N, n, m) fp32
 int ctf_filter(const double* params, int N, int n, int m, double scale, float* out, cudaStream_t st);

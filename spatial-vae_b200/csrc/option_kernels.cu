@@ -226,4 +226,27 @@ template int coord_row_grad_opt<float>(int, const float*, int, int, int, int, co
 template int coord_row_grad_opt<__nv_bfloat16>(int, const __nv_bfloat16*, int, int, int, int, const float*, long,
                                                const float*, float*, cudaStream_t);
 
+// ---- ResidLinear on the tensor-core path (SVAE_RESID_TC=1): the forward adds the layer input exactly in the GEMM
+// epilogue; the dX GEMM sees W + I (a bf16 copy with the identity added: the rounding of the diagonal only touches
+// the gradient, well inside its tolerance); the encoder's 3-term bf16 GEMMs see an fp32 copy of W + I.
+__global__ void add_identity_bf16_k(const float* __restrict__ src, int n, __nv_bfloat16* __restrict__ dst, int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(long)i * ld + i] = __float2bfloat16_rn(src[(long)i * n + i] + 1.f);
+}
+int add_identity_bf16(const float* src, int n, __nv_bfloat16* dst, int ld, cudaStream_t st) {
+    add_identity_bf16_k<<<ceil_div(n, 256), 256, 0, st>>>(src, n, dst, ld);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+__global__ void copy_add_identity_k(const float* __restrict__ src, int n, float* __restrict__ dst) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * n) return;
+    dst[i] = src[i] + ((int)(i / n) == (int)(i % n) ? 1.f : 0.f);
+}
+int copy_add_identity(const float* src, int n, float* dst, cudaStream_t st) {
+    copy_add_identity_k<<<ceil_div((long)n * n, 256), 256, 0, st>>>(src, n, dst);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
 }  // namespace svae

@@ -8,6 +8,7 @@
 //
 //   mode 0  FWD : out[M,N]  = act(A[M,K] W[N,K]^T + bias)              A K-major,  B K-major
 //                 (+ optional fused output layer: o[m,c] += sum_n h[m,n] W_o[c,n])
+//                 (RES: ResidLinear, out = act(A W^T + bias + R) with the residual tile R streamed into the epilogue)
 //   mode 1  DX  : out[M,N]  = (A[M,K] W[K,N]) .* act'(aux[M,N])        A K-major,  B MN-major
 //                 (RED: instead of storing, reduce per image: S[b,{1,x,y},n] += sum_p out[b*P+p, n] {1,x_p,y_p})
 //   mode 2  DW  : outf[M,N] += A[Kr,M]^T Bm[Kr,N]  (split over Kr)     A MN-major, B MN-major
@@ -32,6 +33,9 @@ __host__ __device__ constexpr int epi_groups(int cg) { return (void)cg, 1; }
 __host__ __device__ constexpr int num_threads(int cg) { return 128 + 128 * epi_groups(cg); }
 __host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }        // 32 KB | 16 KB
 __host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
+// Layout index of a kernel variant: its MODE, or 3 for the forward GEMM with a residual stream (mode 0 + the aux
+// staging blocks of mode 1).
+constexpr int LAYOUT_FWD_RES = 3;
 // ring depth: whatever the staging blocks leave (mode 1 needs aux blocks too)
 __host__ __device__ constexpr int stages_of(int cg, int mode) {
     return cg == 2 ? ((mode == 1 && epi_groups(cg) == 2) ? 3 : 4) : 3;
@@ -44,11 +48,11 @@ __host__ __device__ constexpr int off_aux_stage(int cg, int mode) {
     return off_out_stage(cg, mode) + (mode == 2 ? 0 : 2 * epi_groups(cg) * EPI_BLOCK_BYTES);
 }
 __host__ __device__ constexpr int off_tables(int cg, int mode) {
-    return off_aux_stage(cg, mode) + (mode == 1 ? 2 * epi_groups(cg) * EPI_BLOCK_BYTES : 0);
+    return off_aux_stage(cg, mode) + ((mode == 1 || mode == LAYOUT_FWD_RES) ? 2 * epi_groups(cg) * EPI_BLOCK_BYTES : 0);
 }
 constexpr int RED_TABLE_BYTES = 128 * 8 + 128 * 2;    // (x,y) float2 per row + int16 image index per row
 __host__ __device__ constexpr int table_bytes(int mode) {
-    return mode == 0 ? 2 * (1 + MAX_DOT_C) * BN * 4 : (mode == 1 ? 2 * RED_TABLE_BYTES : 0);
+    return (mode == 0 || mode == LAYOUT_FWD_RES) ? 2 * (1 + MAX_DOT_C) * BN * 4 : (mode == 1 ? 2 * RED_TABLE_BYTES : 0);
 }
 __host__ __device__ constexpr int off_bars(int cg, int mode) { return off_tables(cg, mode) + table_bytes(mode); }
 // The dynamic shared memory is declared 1024-byte aligned; the pair dX kernel has no room for alignment slack
@@ -58,7 +62,8 @@ __host__ __device__ constexpr int align_slack(int cg, int mode) {
 }
 __host__ __device__ constexpr int smem_bytes(int cg, int mode) { return off_bars(cg, mode) + 256 + align_slack(cg, mode); }
 static_assert(smem_bytes(1, 0) <= 232448 && smem_bytes(1, 1) <= 232448 && smem_bytes(2, 0) <= 232448 &&
-              smem_bytes(2, 1) <= 232448 && smem_bytes(2, 2) <= 232448, "shared memory budget");
+              smem_bytes(2, 1) <= 232448 && smem_bytes(2, 2) <= 232448 && smem_bytes(1, LAYOUT_FWD_RES) <= 232448 &&
+              smem_bytes(2, LAYOUT_FWD_RES) <= 232448, "shared memory budget");
 constexpr unsigned long long WAIT_TIMEOUT_CYCLES = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
@@ -70,6 +75,7 @@ struct TcParams {
     void* out; int ldo;
     int vec_red;              // mode 2: 16-byte aligned rows -> red.global.add.v4.f32
     int out_f32;              // modes 0/1: fp32 output (and fp32 aux) instead of bf16
+    int res;                  // mode 0: a bf16 residual tile is added before the activation (ResidLinear)
     // mode 0, optional: fused output layer (models.py:84): o_accum[m, c] += sum_n h[m,n] * out_w[c, n]
     const float* out_w; int out_w_ld; int dot_c; float* o_accum;
     // mode 1 RED: per-image moments of the result instead of storing it
@@ -248,11 +254,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // OUT32: modes 0/1 write fp32 (and read an fp32 aux matrix) instead of bf16: used by the encoder, whose
 // fp32 GEMMs run as three bf16 MMAs on hi/lo splits of the operands (error-compensated, ~fp32 accuracy).
 // RED: mode 1 only: per-image column moments of the result instead of storing it.
-template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED>
+// RES: mode 0, bf16 only: out = act(acc + bias + R), R (M x N, bf16) streamed by TMA into the epilogue like dX's aux.
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED, bool RES = false>
 __global__ void __launch_bounds__(num_threads(CG), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
-    constexpr int STAGES = stages_of(CG, MODE);
+    static_assert(!RES || (MODE == 0 && !OUT32 && DOTC == 0), "the residual stream exists for the plain bf16 forward");
+    constexpr int LM = RES ? LAYOUT_FWD_RES : MODE;      // shared-memory layout of this variant
+    constexpr bool AUX = (MODE == 1) || RES;             // an M x N tile is streamed into the epilogue
+    constexpr int STAGES = stages_of(CG, LM);
     constexpr int B_STAGE_BYTES = b_stage_bytes(CG);
     constexpr int STAGE_BYTES = stage_bytes(CG);
     constexpr int BN_CTA = BN / CG;                // B-tile rows (N) staged by this CTA
@@ -263,11 +273,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles (same offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (align_slack(CG, MODE) == 0 && smem != smem_raw) __trap();
+    if (align_slack(CG, LM) == 0 && smem != smem_raw) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    float* s_tab = reinterpret_cast<float*>(smem + off_tables(CG, MODE));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars(CG, MODE));
+    float* s_tab = reinterpret_cast<float*>(smem + off_tables(CG, LM));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars(CG, LM));
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux_full[2*EG], then the tmem base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * EG);
 
@@ -285,7 +295,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (MODE != 2 && !RED) tma_prefetch_desc(&tmOut);
-        if (MODE == 1) tma_prefetch_desc(&tmAux);
+        if (AUX) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
@@ -433,8 +443,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // act[l-1] block in by TMA, two of the group's blocks ahead.
             constexpr int BCOLS = OUT32 ? 32 : 64;         // columns per 128-byte-wide staging block
             constexpr int HALVES = OUT32 ? 1 : 2;          // 32-column TMEM loads per block
-            uint8_t* out_stage = smem + off_out_stage(CG, MODE) + eg * 2 * EPI_BLOCK_BYTES;
-            uint8_t* aux_stage = smem + off_aux_stage(CG, MODE) + eg * 2 * EPI_BLOCK_BYTES;
+            uint8_t* out_stage = smem + off_out_stage(CG, LM) + eg * 2 * EPI_BLOCK_BYTES;
+            uint8_t* aux_stage = smem + off_aux_stage(CG, LM) + eg * 2 * EPI_BLOCK_BYTES;
             const uint32_t auxfull_g = auxfull0 + 8 * (2 * eg);
             uint32_t blk = 0;                              // this group's running block counter (buffer = blk & 1)
             uint32_t tile_it = 0;                          // tiles processed (parity selects the table copy)
@@ -457,7 +467,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ++pf_blk;
                 pf_jb += EG;
             };
-            if (MODE == 1 && leader) { prefetch_aux(); prefetch_aux(); }
+            if (AUX && leader) { prefetch_aux(); prefetch_aux(); }
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++tile_it) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
@@ -507,7 +517,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t buf = blk & 1;
                     uint8_t* ostage = out_stage + buf * EPI_BLOCK_BYTES;
                     const uint8_t* astage = aux_stage + buf * EPI_BLOCK_BYTES;
-                    if (MODE == 1) mbar_wait(auxfull_g + 8 * buf, (blk >> 1) & 1);
+                    if (AUX) mbar_wait(auxfull_g + 8 * buf, (blk >> 1) & 1);
                     // the TMA store issued two blocks ago must have finished READING this staging buffer
                     if (!RED && leader) tma_store_wait_read<1>();
                     epi_bar_sync(eg);
@@ -540,7 +550,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         } else {
                             uint4 auxv[4];
-                            if (MODE == 1) {
+                            if (AUX) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
                                     auxv[j] = *reinterpret_cast<const uint4*>(astage + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4));
@@ -550,7 +560,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (MODE == 0) {
 #pragma unroll
                                 for (int j4 = 0; j4 < 8; ++j4) {          // 4 columns at a time: 128-bit table reads
-                                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + tc + 4 * j4);
+                                    float4 bv = *reinterpret_cast<const float4*>(s_bias + tc + 4 * j4);
+                                    if (RES) {                             // + the layer input (skip connection)
+                                        const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv);
+                                        const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&aw[2 * j4]);
+                                        const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&aw[2 * j4 + 1]);
+                                        bv.x += __low2float(r01); bv.y += __high2float(r01);
+                                        bv.z += __low2float(r23); bv.w += __high2float(r23);
+                                    }
                                     const float hh[4] = {
                                         act_const<ACT>(__uint_as_float(v[4 * j4 + 0]) + bv.x),
                                         act_const<ACT>(__uint_as_float(v[4 * j4 + 1]) + bv.y),
@@ -589,7 +606,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * BCOLS, m_cta);   // clips rows >= M
                             tma_store_commit();
                         }
-                        if (MODE == 1) prefetch_aux();     // aux buffer `buf` is free again
+                        if (AUX) prefetch_aux();           // aux buffer `buf` is free again
                     }
                     if (RED) {
                         // per-image moments of this 128 x 64 bf16 block: thread = (column pair, 32-row quarter)
@@ -679,19 +696,20 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
     return SVAE_OK;
 }
 
-template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED>
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED, bool RES = false>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x, const TcParams& p,
            int grid, cudaStream_t st) {
     static bool configured = false;
-    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG, OUT32, RED>;
+    constexpr int LM = RES ? LAYOUT_FWD_RES : MODE;
+    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG, OUT32, RED, RES>;
     if (!configured) {
-        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG, MODE)));
+        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG, LM)));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(num_threads(CG));
-    cfg.dynamicSmemBytes = smem_bytes(CG, MODE);
+    cfg.dynamicSmemBytes = smem_bytes(CG, LM);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -713,6 +731,9 @@ int launch_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap
     (cg == 2 ? launch<M_, ACT, D_, 2, O_, R_>(a, b, o, x, p, grid, st)                          \
              : launch<M_, ACT, D_, 1, O_, R_>(a, b, o, x, p, grid, st))
     if (MODE == 0) {
+        if (p.res)
+            return cg == 2 ? launch<0, ACT, 0, 2, false, false, true>(a, b, o, x, p, grid, st)
+                           : launch<0, ACT, 0, 1, false, false, true>(a, b, o, x, p, grid, st);
         if (p.out_f32) return SVAE_TC_LAUNCH(0, 0, true, false);
         if (p.o_accum == nullptr) return SVAE_TC_LAUNCH(0, 0, false, false);
         if (p.dot_c == 1) return SVAE_TC_LAUNCH(0, 1, false, false);
@@ -770,6 +791,7 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     p.act = act; p.out = out; p.ldo = ldo;
     p.out_w = ex.out_w; p.out_w_ld = ex.out_w_ld; p.dot_c = ex.dot_c; p.o_accum = ex.o_accum;
     p.out_f32 = (ex.out_f32 && mode != 2) ? 1 : 0;
+    p.res = (mode == 0 && ex.resid != nullptr) ? 1 : 0;
     p.red_S = (mode == 1) ? ex.red_S : nullptr; p.red_ld = ex.red_ld; p.red_grid = ex.red_grid;
     p.red_P = ex.red_P; p.red_b0 = ex.red_b0;
     const bool f32 = p.out_f32 != 0;
@@ -793,6 +815,11 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, N, K, ldw, 64, 256 / cg));
         SVAE_TRY(make_map(&mo, out, M, N, ldo, ebox, 128, f32));
+        if (p.res) {
+            SVAE_REQUIRE(!f32 && ex.o_accum == nullptr, SVAE_EINVAL,
+                         "tc_gemm fwd: the residual stream exists for the plain bf16 forward (no fp32 output, no fused dot)");
+            SVAE_TRY(make_map(&mx, ex.resid, M, N, ex.ld_resid, 64, 128));
+        }
     } else if (mode == 1) {
         SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm dx: N, K must be multiples of 64");
         SVAE_REQUIRE(aux != nullptr, SVAE_EINVAL, "tc_gemm dx: aux is required");

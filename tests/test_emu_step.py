@@ -278,3 +278,22 @@ def test_integration_md_ctypes_stub_works_as_written(emu):
     for i, (g, r) in enumerate(zip(grads, ref)):
         assert float((g - r).abs().max()) <= 3e-2 * (float(r.abs().max()) + 1e-6), i
     assert len(dec_params) == 7
+
+
+@pytest.mark.parametrize("name,sms", [("particles_opt_resid", "148"), ("particles_opt_all", "2")])
+def test_emulated_resid_on_the_tensor_core_route(monkeypatch, tmp_path, name, sms):
+    """SVAE_RESID_TC=1: ResidLinear layers on the tcgen05 GEMMs (tc_gemm RES: the layer input tile is streamed into
+    the forward epilogue and added before the activation; dX sees a bf16 W + I copy; the encoder's 3-term GEMMs see
+    fp32 W + I).  Runs the real kernel on the host model of tests/simt_emu/tc_emu.h, on a 148-SM and on a 2-SM
+    emulated device (several tiles per persistent CTA pair), against the reference-generated fixtures."""
+    monkeypatch.setenv("SVAE_RESID_TC", "1")
+    monkeypatch.setenv("SVAE_EMU_SMS", sms)
+    emu_backend.install(monkeypatch, fresh_copy_dir=tmp_path)     # the switches are read once per loaded library
+    d = load_case(name)
+    dec, enc = oracle_params(d)
+    cfg = option_cfg(d)
+    grid, y, eps, kw = _inputs(d)
+    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "fast", **kw)
+    assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= 1e-3 * abs(float(d["elbo"])) + 1e-4
+    for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
+        assert float((g - r).abs().max()) <= 5e-2 * (float(r.abs().max()) + 1e-6), f"{name} grad {i}"

@@ -462,3 +462,22 @@ def _run_fuzz_step(seed):
             for i, (a, b) in enumerate(zip(grads, ograds)):
                 lim = 2e-3 * float(b.abs().max()) + 2e-6
                 assert float((a - b).abs().max()) <= lim, (c, i, float((a - b).abs().max()), lim)
+
+
+def test_resid_on_the_tensor_core_route_in_a_subprocess():
+    """SVAE_RESID_TC=1 (read once per process, hence the subprocess): the ResidLinear fixtures, the resid module tests
+    and the option trainer trajectory again with the skip connection added in the tcgen05 forward epilogue
+    (tc_gemm RES) instead of running the fp32 kernels."""
+    import subprocess
+    import sys
+    _cuda()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SVAE_RESID_TC="1")
+    sel = ("(golden_fast_precision and (resid or opt_all)) or "
+           "(modules_forward_backward and fast and (True-False-False or True-True-True))")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", sel], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=1200)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-20:])
+    assert r.returncode == 0 and " passed" in r.stdout and " failed" not in r.stdout, tail
+    assert "4 passed" in r.stdout, tail
