@@ -74,6 +74,7 @@ void run_cluster(std::function<void()>& body, int per_cta, int cluster, unsigned
     s.per_cta = per_cta;
     s.cluster = cluster;
     s.first_block = first_block;
+    s.dyn_req = smem;
     const int n = per_cta * cluster;
     s.n = n;
     if ((int)s.ctx.size() < n) {

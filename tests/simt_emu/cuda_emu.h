@@ -114,7 +114,8 @@ struct State {
     int cur = 0;                      // running fiber
     unsigned first_block = 0;         // blockIdx.x of CTA 0 of the running cluster
     std::vector<void*> dyn;           // dynamic shared memory arena of each CTA of the cluster
-    size_t dyn_cap = 0;
+    size_t dyn_cap = 0;               // allocated bytes per arena
+    size_t dyn_req = 0;               // bytes the running launch asked for
     int cta() const { return cur / per_cta; }
     int tid() const { return cur % per_cta; }
 };

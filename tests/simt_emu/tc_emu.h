@@ -21,7 +21,14 @@ inline uint32_t smem_u32(const void* p) {
     if (off < 0 || off >= (ptrdiff_t)(1 << 18)) { fprintf(stderr, "tc_emu: pointer outside the CTA's shared memory\n"); abort(); }
     return ((uint32_t)c << 24) | (uint32_t)off;
 }
-inline char* smem_ptr(uint32_t addr) { return (char*)svae_emu::dyn_smem_of((int)(addr >> 24)) + (addr & 0xFFFFFF); }
+inline char* smem_ptr(uint32_t addr) {
+    if ((addr & 0xFFFFFF) >= svae_emu::state().dyn_req || (int)(addr >> 24) >= svae_emu::state().cluster) {
+        fprintf(stderr, "tc_emu: shared-memory address %#x outside the %zu bytes the launch asked for\n", addr,
+                svae_emu::state().dyn_req);
+        abort();
+    }
+    return (char*)svae_emu::dyn_smem_of((int)(addr >> 24)) + (addr & 0xFFFFFF);
+}
 inline uint32_t swz128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }      // SWIZZLE_128B on address bits
 
 // ---- mbarrier -------------------------------------------------------------------------------------------------------
