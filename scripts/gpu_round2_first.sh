@@ -17,4 +17,9 @@ set -o pipefail
     SVAE_CTF_FAST=$v timeout 300 python bench.py --config c5 --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ctf_fast=$v', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
   done
+  echo "== C2: images per decoder pass (L2 residency: one (rows x 512) bf16 matrix is 0.8 MB per image; 126 MB L2)"
+  for ch in 0 512 256 128 64 32; do
+    timeout 300 python bench.py --config c2 --chunk $ch --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('chunk=$ch', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
+  done
 } | tee gpurun_out/round2_first.log

@@ -166,3 +166,48 @@ def test_random_module_configuration_matches_oracle(emu, seed):
         assert g is not None, (cfg, i)
         lim = 1e-3 * float(rr.abs().max()) + 2e-6
         assert float((g - rr).abs().max()) <= lim, (cfg, i, float((g - rr).abs().max()), lim)
+
+
+@pytest.mark.parametrize("sms", ["148", "3"])
+def test_random_tcgen05_gemm_shapes_on_the_host_model(monkeypatch, tmp_path, sms):
+    """svae_gemm_bf16 (tc_gemm.cu on the tcgen05 host model) for random shapes: ragged M below and above one pair
+    tile, every multiple of 64 up to 384 for N and K, all three modes, on a 148-SM and on a 3-SM emulated device (odd
+    number of SMs: one CTA pair only, so every tile goes through the same persistent pair)."""
+    import spatial_vae.functional as SF
+    monkeypatch.setenv("SVAE_EMU_SMS", sms)
+    emu_backend.install(monkeypatch, fresh_copy_dir=tmp_path)
+    r = np.random.default_rng(int(sms))
+    g = torch.Generator().manual_seed(int(sms))
+    for case in range(14):
+        M = int(r.choice([1, 7, 127, 128, 129, 255, 256, 257, 300, 513]))
+        N, K = int(r.choice([64, 128, 192, 320, 384])), int(r.choice([64, 128, 256, 384]))
+        mode = case % 3
+        if mode == 2:
+            # dW: outf[M2, N2] += A[Kr, M2]^T B[Kr, N2] with ragged output sizes and a ragged reduction length
+            Kr, M2, N2 = int(r.choice([5, 64, 200, 700])), int(r.choice([30, 64, 100])), int(r.choice([17, 64, 130]))
+            lda, ldb = (M2 + 63) // 64 * 64, (N2 + 63) // 64 * 64
+            A = torch.zeros(Kr, lda, dtype=torch.bfloat16)
+            Bm = torch.zeros(Kr, ldb, dtype=torch.bfloat16)
+            A[:, :M2] = (torch.randn(Kr, M2, generator=g) * 0.3).bfloat16()
+            Bm[:, :N2] = (torch.randn(Kr, N2, generator=g) * 0.3).bfloat16()
+            out = torch.randn(M2, N2, generator=g)
+            ref = out + A[:, :M2].float().t() @ Bm[:, :N2].float()
+            SF.gemm_bf16(2, A, Bm, M=M2, N=N2, K=Kr, out=out)
+            np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-4, atol=1e-4, err_msg=f"dw {Kr} {M2} {N2}")
+            continue
+        A = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16)
+        if mode == 0:
+            W = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+            bias = torch.randn(N, generator=g)
+            act = int(r.integers(0, 4))
+            SF.gemm_bf16(0, A, W, M=M, N=N, K=K, bias=bias, activation=act, out=out)
+            pre = A.float() @ W.float().t() + bias
+            ref = [torch.tanh, lambda t: torch.where(t > 0, t, 0.01 * t), torch.relu, torch.sigmoid][act](pre)
+        else:
+            W = (torch.randn(K, N, generator=g) / math.sqrt(K)).bfloat16()
+            aux = torch.tanh(torch.randn(M, N, generator=g)).bfloat16()
+            SF.gemm_bf16(1, A, W, M=M, N=N, K=K, aux=aux, activation=0, out=out)
+            ref = (A.float() @ W.float()) * (1 - aux.float() ** 2)
+        assert torch.isfinite(out.float()).all(), (mode, M, N, K)
+        np.testing.assert_allclose(out.float().numpy(), ref.numpy(), rtol=2e-2, atol=2e-2, err_msg=f"{mode} {M} {N} {K}")
