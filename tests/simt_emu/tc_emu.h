@@ -79,17 +79,40 @@ inline void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int 
 inline void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
     tma_load_2d(dst, map, leader_bar, c0, c1);
 }
-inline void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+// TMA stores are modelled as LATE as the program allows: the copy out of shared memory is only performed when the
+// issuing thread's cp.async.bulk.wait_group.read requires it (or at wait_group 0).  A staging buffer that is
+// overwritten before that point therefore corrupts the output here, as it may on the hardware.
+struct PendingStore { CUtensorMap map; uint32_t src; int c0, c1; };
+struct StoreQueue { std::vector<std::vector<PendingStore>> groups; std::vector<PendingStore> open; };
+inline StoreQueue& store_queue() {
+    static std::map<int, StoreQueue> q;
+    return q[svae_emu::state().cur];
+}
+inline void tma_store_perform(const PendingStore& p) {
+    const CUtensorMap* m = &p.map;
     for (uint32_t r = 0; r < m->box_rows; ++r)
         for (uint32_t e = 0; e < m->box_cols; ++e) {
-            const long row = (long)c1 + r, col = (long)c0 + e;
+            const long row = (long)p.c1 + r, col = (long)p.c0 + e;
             if (row >= (long)m->rows || col >= (long)m->cols) continue;        // clipped
-            const uint32_t a = (src & 0xFFFFFF) + r * 128 + e * m->esize;
-            memcpy(m->base + row * m->row_pitch + col * m->esize, smem_ptr((src & 0xFF000000u) | swz128(a)), m->esize);
+            const uint32_t a = (p.src & 0xFFFFFF) + r * 128 + e * m->esize;
+            memcpy(m->base + row * m->row_pitch + col * m->esize, smem_ptr((p.src & 0xFF000000u) | swz128(a)), m->esize);
         }
 }
-inline void tma_store_commit() {}
-template <int N> inline void tma_store_wait_read() {}
+inline void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    store_queue().open.push_back(PendingStore{*m, src, c0, c1});
+}
+inline void tma_store_commit() {
+    StoreQueue& q = store_queue();
+    q.groups.push_back(std::move(q.open));
+    q.open.clear();
+}
+template <int N> inline void tma_store_wait_read() {          // at most N of the most recent groups may still be reading
+    StoreQueue& q = store_queue();
+    while ((int)q.groups.size() > N) {
+        for (const PendingStore& p : q.groups.front()) tma_store_perform(p);
+        q.groups.erase(q.groups.begin());
+    }
+}
 
 // ---- cluster ----------------------------------------------------------------------------------------------------------
 inline uint32_t cluster_ctarank() { return (uint32_t)svae_emu::state().cta(); }
