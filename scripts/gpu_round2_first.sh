@@ -18,7 +18,8 @@ set -o pipefail
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ctf_fast=$v', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
   done
   echo "== C2: images per decoder pass (L2 residency: one (rows x 512) bf16 matrix is 0.8 MB per image; 126 MB L2)"
-  for ch in 0 512 256 128 64 32; do
+  # 24 / 48 / 96 images = 18816 / 37632 / 75264 rows = 148 / 294 / 588 pair tiles = 2 / ~4 / ~8 full waves of 74 CTA pairs
+  for ch in 0 512 256 96 48 24; do
     timeout 300 python bench.py --config c2 --chunk $ch --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('chunk=$ch', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
   done
