@@ -17,6 +17,11 @@ set -o pipefail
     SVAE_CTF_FAST=$v timeout 300 python bench.py --config c5 --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ctf_fast=$v', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
   done
+  echo "== C2: dual-stream chunk schedule (SVAE_DUAL_STREAM=1) against the default, eager and graphed"
+  for v in 0 1; do for g in "" "--no-graph"; do
+    SVAE_DUAL_STREAM=$v timeout 300 python bench.py --config c2 --steps 100 --warmup 5 --no-cpu-baseline $g 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('dual_stream=$v $g', round(d['ms_per_step'],3), 'ms/step')"
+  done; done
   echo "== C2: images per decoder pass (L2 residency: one (rows x 512) bf16 matrix is 0.8 MB per image; 126 MB L2)"
   # 24 / 48 / 96 images = 18816 / 37632 / 75264 rows = 148 / 294 / 588 pair tiles = 2 / ~4 / ~8 full waves of 74 CTA pairs
   for ch in 0 512 256 96 48 24; do

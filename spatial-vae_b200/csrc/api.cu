@@ -46,12 +46,48 @@ struct Plan {
     size_t weff = 0, dlat = 0, enc_wres = 0;
     bool resid_tc = false;          // ResidLinear layers on the tensor-core GEMMs: wbf16 also holds the W + I copies
     long w_img_stride = 0;
+    // chunk-local buffers (o, g_o, acts, delta) exist `sets` times, `set_stride` bytes apart: with two sets the
+    // chunks alternate between two streams so the bandwidth-bound passes of one overlap the GEMMs of the other
+    int sets = 1;
+    size_t set_stride = 0;
 };
 
 static size_t take(size_t& cur, size_t bytes) {
     size_t off = cur;
     cur += (bytes + 1023) / 1024 * 1024;
     return off;
+}
+
+// SVAE_DUAL_STREAM=1: process the image chunks of a step alternately on the caller's stream and an auxiliary one
+static bool dual_stream_enabled() {
+    static const bool on = (getenv("SVAE_DUAL_STREAM") != nullptr && getenv("SVAE_DUAL_STREAM")[0] == '1');
+    return on;
+}
+
+// smaller minibatches are not worth splitting (SVAE_DUAL_STREAM_MIN_B overrides the threshold, for tests)
+static int dual_stream_min_batch() {
+    static const int n = getenv("SVAE_DUAL_STREAM_MIN_B") != nullptr ? atoi(getenv("SVAE_DUAL_STREAM_MIN_B")) : 128;
+    return n;
+}
+
+struct AuxStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+// one auxiliary stream + two events per device, created on first use and kept for the life of the process
+static int get_aux_stream(AuxStream** out) {
+    static AuxStream table[16];
+    int dev = 0;
+    SVAE_CUDA(cudaGetDevice(&dev));
+    SVAE_REQUIRE(dev >= 0 && dev < 16, SVAE_EINVAL, "device index %d out of range", dev);
+    AuxStream& a = table[dev];
+    if (a.stream == nullptr) {
+        SVAE_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        SVAE_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+        SVAE_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+    }
+    *out = &a;
+    return SVAE_OK;
 }
 
 static int validate(const SvaeShape& s, const SvaeConfig& c) {
@@ -112,6 +148,15 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     }
     if (chunk > s.B) chunk = s.B;
     if (chunk < 1) chunk = 1;
+    p.sets = 1;
+    if (fast && dual_stream_enabled() && s.B >= dual_stream_min_batch()) {
+        // an even number of chunks, two buffer sets
+        int n_chunks = ceil_div(s.B, chunk);
+        if (n_chunks < 2) n_chunks = 2;
+        if (n_chunks & 1) ++n_chunks;
+        chunk = ceil_div(s.B, n_chunks);
+        p.sets = 2;
+    }
     p.chunk = chunk;
     const size_t B = (size_t)(s.B > 0 ? s.B : 1), I = (size_t)s.I, rows = (size_t)chunk * s.P;
     size_t cur = 0;
@@ -150,6 +195,8 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.acts = take(cur, p.act_stride * s.L);
     p.delta_stride = p.act_stride;
     p.delta = take(cur, p.delta_stride * 2);
+    p.set_stride = cur - p.o;
+    if (p.sets == 2) cur += p.set_stride;
     p.w_stride = (size_t)p.Hp * p.Hp * 2;
     // bf16 hidden weights; with resid_tc a second set with the identity added follows (operands of the dX GEMMs)
     p.wbf16 = take(cur, fast ? p.w_stride * (s.L > 1 ? s.L - 1 : 1) * (p.resid_tc ? 2 : 1) : 0);
@@ -333,8 +380,11 @@ struct DecoderCtx {
     const Plan* p;
     char* ws;
     cudaStream_t st;
-    T* act(int l) const { return reinterpret_cast<T*>(ws + p->acts + p->act_stride * l); }
-    T* delta(int i) const { return reinterpret_cast<T*>(ws + p->delta + p->delta_stride * i); }
+    size_t set_off = 0;      // byte offset of this chunk's buffer set (o, g_o, acts, delta)
+    T* act(int l) const { return reinterpret_cast<T*>(ws + set_off + p->acts + p->act_stride * l); }
+    T* delta(int i) const { return reinterpret_cast<T*>(ws + set_off + p->delta + p->delta_stride * i); }
+    float* logits() const { return reinterpret_cast<float*>(ws + set_off + p->o); }
+    float* g_logits() const { return reinterpret_cast<float*>(ws + set_off + p->g_o); }
     float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
     __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
     // operand of the dX GEMM of hidden layer l+1: W, or the W + I copy for ResidLinear layers on tensor cores
@@ -362,9 +412,9 @@ template <>
 int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const SvaeDecoderParams& dp, int l, int rows,
                                   bool fuse_out) {
     const int Hp = d.p->Hp;
-    if (fuse_out) SVAE_TRY(fill_rows(d.f(d.p->o), dp.out_b, rows, d.s->C, d.s->C, d.st));
+    if (fuse_out) SVAE_TRY(fill_rows(d.logits(), dp.out_b, rows, d.s->C, d.s->C, d.st));
     TcExtra ex;
-    if (fuse_out) { ex.out_w = dp.out_w; ex.out_w_ld = d.s->H; ex.dot_c = d.s->C; ex.o_accum = d.f(d.p->o); }
+    if (fuse_out) { ex.out_w = dp.out_w; ex.out_w_ld = d.s->H; ex.dot_c = d.s->C; ex.o_accum = d.logits(); }
     if (d.p->resid_tc) { ex.resid = d.act(l - 1); ex.ld_resid = Hp; }      // act(W h + b + h), h added in the epilogue
     return tc_gemm(0, rows, Hp, Hp, d.act(l - 1), Hp, d.wbf(l - 1), Hp, dp.hidden_b[l - 1], d.s->H, nullptr, 0,
                    d.c->activation, d.act(l), Hp, d.st, ex);
@@ -421,7 +471,7 @@ static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams
     const int Hp = d.p->Hp, rows = nb * s.P;
     if (rows == 0) return SVAE_OK;
     if (std::is_same<T, float>::value && Hp != s.H) {
-        SVAE_CUDA(cudaMemsetAsync(d.ws + d.p->acts, 0, d.p->act_stride * s.L + d.p->delta_stride * 2, d.st));
+        SVAE_CUDA(cudaMemsetAsync(d.ws + d.set_off + d.p->acts, 0, d.p->act_stride * s.L + d.p->delta_stride * 2, d.st));
     }
     if (d.p->opt)
         SVAE_TRY(layer0_opt_forward<T>(d.p->F, s.P, d.c->activation, b0, nb, d.l0_w(dp), d.p->w_img_stride,
@@ -433,8 +483,8 @@ static int decoder_chunk_forward(const DecoderCtx<T>& d, const SvaeDecoderParams
     const bool fuse_out = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3 && !d.p->resid_tc;
     for (int l = 1; l < s.L; ++l) SVAE_TRY(hidden_forward<T>(d, dp, l, rows, fuse_out && l == s.L - 1));
     float* yh = y_hat ? y_hat + (size_t)b0 * s.P * s.C : nullptr;
-    if (fuse_out) return yh ? logits_to_yhat(d.f(d.p->o), yh, (long)rows * s.C, s.C, d.c->softplus, d.st) : SVAE_OK;
-    return out_forward<T>(d.act(s.L - 1), rows, s.H, Hp, s.C, dp.out_w, dp.out_b, d.c->softplus, d.f(d.p->o), yh, d.st);
+    if (fuse_out) return yh ? logits_to_yhat(d.logits(), yh, (long)rows * s.C, s.C, d.c->softplus, d.st) : SVAE_OK;
+    return out_forward<T>(d.act(s.L - 1), rows, s.H, Hp, s.C, dp.out_w, dp.out_b, d.c->softplus, d.logits(), yh, d.st);
 }
 
 // backward over the same chunk given g_o (rows, C) in the workspace: parameter grads, S[b0..]
@@ -445,7 +495,7 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     const int Hp = d.p->Hp, rows = nb * s.P;
     if (rows == 0) return SVAE_OK;
     int cur = 0;
-    SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.f(d.p->g_o), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
+    SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.g_logits(), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
                              g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
     // Optional (SVAE_FUSE_RED=1): the last dX GEMM reduces delta_0 per image in its epilogue (S zero on entry)
     // instead of storing it for image_col_reduce.  Measured in round 1: 704 us vs 482 + 174 us at C2 -- the
@@ -631,11 +681,25 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     if (c.bilinear) SVAE_TRY(bilinear_weights(s, p, dp, d.f(p.zs), d.f(p.weff), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
     if (train && kFast) SVAE_CUDA(cudaMemsetAsync(ws + p.S, 0, (size_t)s.B * p.K1 * p.Hp * sizeof(float), st));
-    for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
+    AuxStream* aux = nullptr;
+    if (p.sets == 2) {
+        SVAE_TRY(get_aux_stream(&aux));
+        SVAE_CUDA(cudaEventRecord(aux->fork, st));               // everything above is done before a chunk starts
+        SVAE_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    }
+    int ci = 0;
+    for (int b0 = 0; b0 < s.B; b0 += p.chunk, ++ci) {
         const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
-        SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, in.grid, nullptr, out.y_hat));
-        SVAE_TRY(likelihood(s, c, b0, nb, d.f(p.o), in.y, in.ctf, in.mask, out.stats, train ? d.f(p.g_o) : nullptr, st));
-        if (train) SVAE_TRY(decoder_chunk_backward<T>(d, dp, *gd, b0, nb, in.grid, nullptr, nullptr));
+        DecoderCtx<T> dc = d;
+        if (p.sets == 2 && (ci & 1)) { dc.st = aux->stream; dc.set_off = p.set_stride; }
+        SVAE_TRY(decoder_chunk_forward<T>(dc, dp, b0, nb, in.grid, nullptr, out.y_hat));
+        SVAE_TRY(likelihood(s, c, b0, nb, dc.logits(), in.y, in.ctf, in.mask, out.stats, train ? dc.g_logits() : nullptr,
+                            dc.st));
+        if (train) SVAE_TRY(decoder_chunk_backward<T>(dc, dp, *gd, b0, nb, in.grid, nullptr, nullptr));
+    }
+    if (p.sets == 2) {
+        SVAE_CUDA(cudaEventRecord(aux->join, aux->stream));
+        SVAE_CUDA(cudaStreamWaitEvent(st, aux->join, 0));
     }
     finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
     SVAE_LAUNCH_CHECK();
@@ -701,7 +765,7 @@ static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, 
         SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, nullptr, x, y_hat));
         if (gd) {
             const long n = (long)nb * s.P * s.C;
-            logit_grad_k<<<ceil_div(n, 256), 256, 0, st>>>(d.f(p.o), g_y + (size_t)b0 * s.P * s.C, d.f(p.g_o), n, s.C,
+            logit_grad_k<<<ceil_div(n, 256), 256, 0, st>>>(d.logits(), g_y + (size_t)b0 * s.P * s.C, d.g_logits(), n, s.C,
                                                            c.softplus);
             SVAE_LAUNCH_CHECK();
             SVAE_TRY(decoder_chunk_backward<T>(d, dp, *gd, b0, nb, nullptr, x, g_x));

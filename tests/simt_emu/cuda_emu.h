@@ -91,6 +91,14 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {
     return cudaSuccess;
 }
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// streams and events: launches execute synchronously in program order, which is one of the orders any stream / event
+// dependency graph allows, so these only hand out distinct handles
+typedef struct CUevent_st* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { static long n = 0; *s = (cudaStream_t)(++n * 64); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { static long n = 0; *e = (cudaEvent_t)(++n * 64); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 
 // ---- built-in variables and the fiber scheduler ------------------------------------------------------
 namespace svae_emu {

@@ -315,3 +315,23 @@ def test_emulated_fused_moment_reduction_variant(monkeypatch, tmp_path, name, fa
     assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= 1e-3 * abs(float(d["elbo"])) + 1e-4
     for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
         assert float((g - r).abs().max()) <= 3e-2 * (float(r.abs().max()) + 1e-6), f"{name} grad {i}"
+
+
+@pytest.mark.parametrize("name,family", [("mnist_rt", "mnist"), ("particles_ctf", "particles"), ("galaxy_rgb", "galaxy"),
+                                         ("particles_opt_all", "particles")])
+def test_emulated_dual_stream_chunk_schedule(monkeypatch, tmp_path, name, family):
+    """SVAE_DUAL_STREAM=1: the image chunks of a step alternate between the caller's stream and an auxiliary one, each
+    with its own set of chunk-local buffers (logits, their gradient, activations, deltas), so the bandwidth-bound SIMT
+    passes of one chunk can overlap the GEMMs of the other.  The emulation runs the launches in program order (one
+    legal order of the two streams): this checks the buffer-set arithmetic and the results, not the overlap."""
+    monkeypatch.setenv("SVAE_DUAL_STREAM", "1")
+    monkeypatch.setenv("SVAE_DUAL_STREAM_MIN_B", "2")
+    emu_backend.install(monkeypatch, fresh_copy_dir=tmp_path)
+    d = load_case(name)
+    dec, enc = oracle_params(d)
+    cfg = option_cfg(d, family) if name in OPTION_CASES else cfg_of(d, family)
+    grid, y, eps, kw = _inputs(d)
+    stats, _, grads = _run(cfg, dec, enc, grid, y, eps, "fast", **kw)
+    assert abs(float(stats[:, 2].mean()) - float(d["elbo"])) <= 1e-3 * abs(float(d["elbo"])) + 1e-4
+    for i, (g, r) in enumerate(zip(grads, golden_grads(d))):
+        assert float((g - r).abs().max()) <= 3e-2 * (float(r.abs().max()) + 1e-6), f"{name} grad {i}"
