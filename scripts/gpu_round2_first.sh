@@ -28,4 +28,9 @@ set -o pipefail
     timeout 300 python bench.py --config c2 --chunk $ch --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | \
       python -c "import sys,json; d=json.loads(sys.stdin.read()); print('chunk=$ch', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
   done
+  echo "== C2: small chunks AND the dual-stream schedule"
+  for ch in 96 48 24; do
+    SVAE_DUAL_STREAM=1 timeout 300 python bench.py --config c2 --chunk $ch --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('dual_stream chunk=$ch', round(d['ms_per_step'],3), 'ms/step', round(d['value']), d['unit'])"
+  done
 } | tee gpurun_out/round2_first.log
