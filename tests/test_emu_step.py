@@ -1,8 +1,8 @@
-"""The library's SIMT kernel sources and host orchestration, executed on the CPU (tests/simt_emu: the .cu files
-compiled with g++ behind a fiber-based SIMT shim) and held to the same golden fixtures and tolerances as the GPU
-parity tests.  This is how kernels written without GPU access are checked before they first run on a B200; it covers
-indexing, reductions, barriers and the call sequence of api.cu, not the tcgen05 GEMM (replaced by a plain-loop
-stand-in) and not GPU-only behaviour (memory model, occupancy, alignment faults beyond 16-byte vector loads).
+"""The library's kernel sources and host orchestration, executed on the CPU (tests/simt_emu: the SIMT .cu files compiled
+with g++ behind a fiber-based shim, tc_gemm.cu on a host model of tcgen05 / TMA / mbarriers) and held to the same golden
+fixtures and tolerances as the GPU parity tests.  This is how kernels written without GPU access are checked before they
+first run on a B200; it covers indexing, reductions, barrier choreography and the call sequence of api.cu, not GPU-only
+behaviour (memory-model races, occupancy, timing).
 """
 import numpy as np
 import pytest
@@ -95,8 +95,8 @@ def test_emulated_option_step_matches_reference_golden(emu, name):
 
 @pytest.mark.parametrize("name,family", CASES + [(n, "particles") for n in OPTION_CASES])
 def test_emulated_step_fast_precision_orchestration(emu, name, family):
-    """FAST precision call sequence (bf16 activations, split3 encoder, fused output dot, bf16 SIMT kernels) with the
-    plain-loop tc_gemm stand-in: north-star tolerance on the ELBO, loose on the gradients."""
+    """FAST precision (bf16 activations, split3 encoder, fused output dot, bf16 SIMT kernels, the tcgen05 GEMM kernel on
+    its host model): north-star tolerance on the ELBO, loose on the gradients."""
     d = load_case(name)
     dec, enc = oracle_params(d)
     cfg = option_cfg(d, family) if name in OPTION_CASES else cfg_of(d, family)
