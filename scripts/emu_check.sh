@@ -10,3 +10,5 @@ for sms in 148 4; do
 done
 echo "== emulated step / fuzz suites"
 python -m pytest tests/test_emu_step.py tests/test_emu_fuzz.py -q -x -p no:cacheprovider
+echo "== bench.py main path on the emulation (about 1.5 minutes)"
+python tests/emu_bench_smoke.py
