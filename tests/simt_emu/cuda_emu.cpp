@@ -94,6 +94,8 @@ void run_cluster(std::function<void()>& body, int per_cta, int cluster, unsigned
         for (int c = 0; c < (cluster > 2 ? cluster : 2); ++c)
             s.dyn.push_back(aligned_alloc(1024, (s.dyn_cap + 1023) / 1024 * 1024 + 1024));
     }
+    // dynamic shared memory starts out as NaN patterns for every block: reads of bytes the block never wrote show up
+    for (int c = 0; c < cluster; ++c) memset(s.dyn[c], 0xFF, smem);
     for (int i = 0; i < n; ++i) {
         getcontext(&s.ctx[i]);
         s.ctx[i].uc_stack.ss_sp = s.stacks[i];
