@@ -1,6 +1,8 @@
 // Fiber scheduler of the SIMT-on-host shim (see cuda_emu.h).  Test infrastructure only.
 #include "cuda_emu.h"
 
+#include <algorithm>
+
 uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};
 dim3 blockDim(1, 1, 1), gridDim(1, 1, 1);
 
@@ -104,9 +106,21 @@ void run_cluster(std::function<void()>& body, int per_cta, int cluster, unsigned
         makecontext(&s.ctx[i], trampoline, 0);
         s.status[i] = RUNNABLE;
     }
+    // SVAE_EMU_SHUFFLE=<seed>: visit the fibers in a different pseudo-random order on every pass instead of by thread
+    // index, to shake out results that depend on which warp happens to run first between two barriers
+    static const char* shuffle_env = getenv("SVAE_EMU_SHUFFLE");
+    static unsigned long long rng = shuffle_env ? strtoull(shuffle_env, nullptr, 10) * 2654435761ull + 1 : 0;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
     for (;;) {
         bool progress = false;
-        for (int i = 0; i < n; ++i) {
+        if (shuffle_env)
+            for (int i = n - 1; i > 0; --i) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i], order[(int)((rng >> 33) % (unsigned long long)(i + 1))]);
+            }
+        for (int oi = 0; oi < n; ++oi) {
+            const int i = order[oi];
             if (s.status[i] == WAIT_COND && s.cond[i]()) s.status[i] = RUNNABLE;
             if (s.status[i] != RUNNABLE) continue;
             s.cur = i;
