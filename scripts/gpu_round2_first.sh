@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 set -o pipefail
 {
   echo "== validated suite"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-  echo "== tests that have only run on tests/simt_emu so far"; timeout 900 python -m pytest tests/test_gpu_zz_options.py -m gpu -q 2>&1 | tail -15
+  echo "== tests that have only run on tests/simt_emu so far"; timeout 900 python -m pytest tests/test_gpu_zy_late.py tests/test_gpu_zz_options.py -m gpu -q 2>&1 | tail -15
   echo "== ResidLinear on the tcgen05 route (SVAE_RESID_TC=1), A/B on a resid network"
   SVAE_RESID_TC=1 timeout 600 python -m pytest tests/test_gpu_zz_options.py -m gpu -q -k "resid or opt_all" 2>&1 | tail -4
   echo "== CTF fast kernel parity"; SVAE_CTF_FAST=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "ctf" 2>&1 | tail -5

@@ -20,7 +20,7 @@ def test_gpu_test_bodies_pass_on_the_simt_emulation():
     env = dict(os.environ, SVAE_TEST_BACKEND="emu")
     env.pop("SVAE_CTF_FAST", None)
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_api.py", "tests/test_gpu_parity.py",
-           "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", DESELECT]
+           "tests/test_gpu_zy_late.py", "tests/test_gpu_zz_options.py", "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", DESELECT]
     try:                                    # four workers when pytest-xdist is available (each loads its own library)
         import xdist  # noqa: F401
         cmd += ["-n", "4"]
