@@ -24,6 +24,8 @@ SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu", "ingest
 # SVAE_EMU_TC=ref: the plain-loop stand-in tc_gemm_ref.cpp (much faster, exercises only the call sequence)
 TC_KERNEL = os.environ.get("SVAE_EMU_TC", "kernel") != "ref"
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
+# tensor-core kernel sources and the number of inline red.global.add.v4.f32 statements each contains
+TC_SOURCES = {"tc_gemm.cu": 1}
 
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)<<<(.*?)>>>\(")
 DYN_SMEM = re.compile(r"extern __shared__ (?:__align__\(\d+\) )?(\w+) (\w+)\[\];")
@@ -33,15 +35,19 @@ TIMER = re.compile(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)
 RED_V4 = re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::"l"\((.*?)\), "f"\((.*?)\), "f"\((.*?)\),\s*"f"\((.*?)\), "f"\((.*?)\) : "memory"\);', re.S)
 
 
-def rewrite_tc(text: str) -> str:
-    """tc_gemm.cu: the PTX-wrapper section is replaced by the host model, the one inline red.global.add by atomics."""
+def rewrite_tc_header(text: str) -> str:
+    """tc_ptx.cuh: the PTX-wrapper section is replaced by the host model (tc_emu.h)."""
     a = text.index("// ---- PTX wrappers")
     b = text.index("// ---- descriptors")
-    text = text[:a] + "}  // namespace\n}  // namespace svae\n#include \"tc_emu.h\"\nnamespace svae {\nnamespace {\n" + text[b:]
+    return text[:a] + "}  // namespace\n}  // namespace svae\n#include \"tc_emu.h\"\nnamespace svae {\nnamespace {\n" + text[b:]
+
+
+def rewrite_tc(text: str, expect_red: int) -> str:
+    """tensor-core kernel sources: the inline red.global.add statements become atomics."""
     text, n = RED_V4.subn(lambda m: "{ float* red_p = %s; atomicAdd(red_p, %s); atomicAdd(red_p + 1, %s); "
                                     "atomicAdd(red_p + 2, %s); atomicAdd(red_p + 3, %s); }" % m.groups(), text)
-    if n != 1:
-        raise RuntimeError("simt_emu/build.py: expected exactly one red.global.add.v4.f32 statement in tc_gemm.cu")
+    if n != expect_red:
+        raise RuntimeError(f"simt_emu/build.py: expected {expect_red} red.global.add.v4.f32 statement(s), found {n}")
     return text
 
 
@@ -64,7 +70,7 @@ def newest(paths):
 
 def build(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["tc_gemm.cu"]] + \
+    inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + list(TC_SOURCES) + ["tc_ptx.cuh"]] + \
              [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc_gemm_ref.cpp", "tc_emu.h", "build.py",
                                               "include/cuda.h")] + \
              [os.path.join(ROOT, "include", "svae_b200.h")]
@@ -81,10 +87,13 @@ def build(force: bool = False) -> str:
         units.append(out)
     units.append(os.path.join(HERE, "cuda_emu.cpp"))
     if TC_KERNEL:
-        out = os.path.join(BUILD, "tc_gemm.cpp")
-        with open(os.path.join(CSRC, "tc_gemm.cu")) as src, open(out, "w") as dst:
-            dst.write(rewrite(rewrite_tc(src.read())))
-        units.append(out)
+        with open(os.path.join(CSRC, "tc_ptx.cuh")) as src, open(os.path.join(BUILD, "tc_ptx.cuh"), "w") as dst:
+            dst.write(rewrite(rewrite_tc_header(src.read())))
+        for f, n_red in TC_SOURCES.items():
+            out = os.path.join(BUILD, f.replace(".cu", ".cpp"))
+            with open(os.path.join(CSRC, f)) as src, open(out, "w") as dst:
+                dst.write(rewrite(rewrite_tc(src.read(), n_red)))
+            units.append(out)
     else:
         units.append(os.path.join(HERE, "tc_gemm_ref.cpp"))
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
