@@ -219,6 +219,16 @@ int  svae_gemm_bf16(int mode, int M, int N, int K,
                     const float* bias, const void* aux, int ldaux, int activation,
                     void* out, int ldo, void* stream);
 
+/* Fused tail of the decoder backward (loss.backward() through SpatialGenerator.forward's first layer,
+ * models.py:104-124, train_mnist.py:50-59,70-74): delta_0 = (delta (rows, Hp) * W (Hp, Hp; [j][n])) .* act'(h_0) is
+ * never stored; h_0[row, n] = act(coord_w[n,0] x' + coord_w[n,1] y' + hz[b, n]) is recomputed from the pixel grid
+ * (P, 2) and the per-image transforms img (B, 4) = cos, sin, dx0, dx1, and the per-image column moments
+ * S (B, 3, Hp) += sum_p delta_0 {1, grid_x, grid_y} are accumulated with fp32 atomics (zero S first; summation
+ * order, hence the last bits, varies from run to run).  Building block of svae_step, exposed for tests. */
+int  svae_gemm_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int activation,
+                          const float* grid, const float* img, const float* coord_w, const float* hz, float* S, int P,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -420,8 +420,8 @@ int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Svae
                    d.c->activation, d.act(l), Hp, d.st, ex);
 }
 
-// red: (FAST only) do not store delta_prev; reduce it per image into S on the fly (first layer's sums)
-struct RedSpec { float* S = nullptr; const float* grid = nullptr; int b0 = 0; };
+// red: (FAST only) delta_prev is not stored: the transposed dX GEMM reduces it per image into S (tc_bwd.cu)
+struct RedSpec { TcMoments m; bool on = false; };
 template <typename T>
 static int hidden_backward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l, int rows,
                            const T* delta, T* delta_prev, const RedSpec& red);
@@ -457,10 +457,9 @@ int hidden_backward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Sva
     (void)dp;
     // dW_l (H,H; ld H) += delta^T act[l-1]   (fp32 accumulate, atomics across row splits)
     SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
-    TcExtra ex;
-    if (red.S != nullptr) { ex.red_S = red.S; ex.red_ld = Hp; ex.red_grid = red.grid; ex.red_P = d.s->P; ex.red_b0 = red.b0; }
+    if (red.on) return tc_dx_moments(rows, H, Hp, delta, Hp, d.wbf_dx(l - 1), Hp, d.c->activation, red.m, d.st);
     return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf_dx(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
-                   delta_prev, Hp, d.st, ex);
+                   delta_prev, Hp, d.st);
 }
 
 // forward of the decoder over images [b0, b0+nb): fills act[0..L-1] and logits o; optional y_hat
@@ -497,16 +496,19 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     int cur = 0;
     SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.g_logits(), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
                              g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
-    // Optional (SVAE_FUSE_RED=1): the last dX GEMM reduces delta_0 per image in its epilogue (S zero on entry)
-    // instead of storing it for image_col_reduce.  Measured in round 1: 704 us vs 482 + 174 us at C2 -- the
-    // SIMT reduction in the epilogue costs more than the HBM pass it removes -- so it is off by default.
-    static const bool want_red = (getenv("SVAE_FUSE_RED") != nullptr && getenv("SVAE_FUSE_RED")[0] == '1');
-    const bool fuse_red = want_red && !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr &&
-                          g_x == nullptr && (long)s.B < 32000 && !d.p->opt;
+    // The dX GEMM of the first hidden layer does not store delta_0: it recomputes h_0 and reduces delta_0 per image
+    // into S in its epilogue (tc_bwd.cu).  Explicit coordinates, coordinate gradients and the first-layer options
+    // keep the stored delta_0 and the separate reductions.
+    const bool fuse_red = !std::is_same<T, float>::value && s.L >= 2 && x_explicit == nullptr && g_x == nullptr &&
+                          grid != nullptr && !d.p->opt;
     bool reduced = false;
     for (int l = s.L - 1; l >= 1; --l) {
         RedSpec red;
-        if (fuse_red && l == 1) { red.S = d.f(d.p->S); red.grid = grid; red.b0 = b0; reduced = true; }
+        if (fuse_red && l == 1) {
+            red.on = reduced = true;
+            red.m.grid = grid; red.m.img = d.f(d.p->img); red.m.coord_w = dp.coord_w; red.m.hz = d.f(d.p->hz);
+            red.m.S = d.f(d.p->S); red.m.P = s.P; red.m.b0 = b0;
+        }
         SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1), red));
         cur ^= 1;
         if (l - 1 >= 1) SVAE_TRY(col_sum<T>(d.delta(cur), rows, s.H, Hp, g.hidden_b[l - 2], d.st));
@@ -966,6 +968,15 @@ int svae_ctf_filter(const double* params, int n_particles, int n, int m, double 
 int svae_sm_clock_probe(float* out_mhz, void* stream) {
     SVAE_REQUIRE(out_mhz != nullptr, SVAE_EINVAL, "null argument");
     return clock_probe(out_mhz, (cudaStream_t)stream);
+}
+
+int svae_gemm_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int activation,
+                         const float* grid, const float* img, const float* coord_w, const float* hz, float* S, int P,
+                         void* stream) {
+    SVAE_REQUIRE(delta && W && grid && img && coord_w && hz && S, SVAE_EINVAL, "null argument");
+    TcMoments m;
+    m.grid = grid; m.img = img; m.coord_w = coord_w; m.hz = hz; m.S = S; m.P = P; m.b0 = 0;
+    return tc_dx_moments(rows, H, Hp, delta, ldd, W, ldw, activation, m, (cudaStream_t)stream);
 }
 
 int svae_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,

@@ -115,4 +115,21 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
             int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
             const TcExtra& ex = TcExtra());
 
+
+// ---- fused backward kernels (tc_bwd.cu) ----------------------------------------------------------------
+// First-layer context of the transposed dX GEMM that reduces delta_0 per image instead of storing it:
+// h_0[row, n] = act(coord_w[n,0] x' + coord_w[n,1] y' + hz[b, n]) is recomputed from (grid, img);
+// S[b0 + row / P, {1, c0, c1}, n] += delta_0[row, n] {1, grid[row % P]}   (S zeroed by the caller).
+struct TcMoments {
+    const float* grid = nullptr;      // (P, 2)
+    const float* img = nullptr;       // (B, 4) cos, sin, dx0, dx1
+    const float* coord_w = nullptr;   // (H, 2)
+    const float* hz = nullptr;        // (B, Hp)
+    float* S = nullptr;               // (B, 3, Hp)
+    int P = 0, b0 = 0;
+};
+// delta (rows x Hp, bf16), W (Hp x Hp bf16, [j][n]): S += moments of (delta W) .* act'(h_0)
+int tc_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int act,
+                  const TcMoments& r, cudaStream_t st);
+
 }  // namespace svae

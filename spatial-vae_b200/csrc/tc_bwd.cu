@@ -1,0 +1,326 @@
+// Fused backward kernels of the decoder hidden stack on sm_100a tensor cores (tcgen05 / TMEM / TMA), the part of
+// loss.backward() (train_mnist.py:147-148) that autograd spends on SpatialGenerator.layers (models.py:77-87,126).
+//
+//   dx_red_kernel   delta_0 = (delta_1 W_1) .* act'(h_0) is never written: the GEMM is computed TRANSPOSED
+//                   (D[n, row] = sum_j W_1[j, n] delta_1[row, j], hidden column n along the TMEM lanes, pixel rows
+//                   along the TMEM columns), so every epilogue thread owns ONE hidden column and walks the pixel rows
+//                   serially.  It recomputes h_0[row, n] = act(Wc[n,0] x' + Wc[n,1] y' + hz[b, n]) in registers
+//                   (the first layer, models.py:104-124), multiplies by act', and accumulates the three per-image
+//                   column moments S[b, {1, c0, c1}, n] with no cross-thread communication.
+//                   W_1 stays resident in shared memory (128 KB per CTA at Hp <= 512); only delta_1 streams.
+//                   Replaces: the dX GEMM's store of delta_0, image_col_reduce's pass over it and the h_0 aux stream.
+//
+//   dw_xf_kernel    dW_l += delta_l^T h_{l-1} for the TOP hidden layer with delta_l produced on the fly:
+//                   delta[row, m] = (sum_c g_o[row, c] W_o[c, m]) * act'(h_l[row, m]) is computed by transform warps
+//                   IN the shared-memory operand stage that TMA filled with h_l, then fed to tcgen05.mma; the same
+//                   warps accumulate db_l, dW_o and db_o, and the transformed stage is written out once by TMA as
+//                   delta_l for the dX GEMM.  Replaces out_backward's two passes over (rows x Hp) matrices.
+#include "tc_ptx.cuh"
+
+namespace svae {
+
+namespace {
+
+constexpr int KB = 64;                       // reduction elements per pipeline stage
+constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64 x 64 bf16 TMA box (MN-major operand block)
+constexpr int OP_BYTES = 128 * KB * 2;       // 16 KB: 128 (rows | columns) x 64 of one operand of one CTA
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant
+constexpr int BW_THREADS = 128 + 32 * EPI_WARPS;
+
+// ---------------------------------------------------------------------------------------------------------------
+// dx_red_kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DR_TILE_N = 256;               // hidden columns per CTA-pair tile (MMA M; 128 TMEM lanes per CTA)
+constexpr int DR_TILE_R = 256;               // pixel rows per tile (MMA N; each CTA stages 128 of them)
+constexpr int DR_SLAB_BYTES = 8 * OP_BYTES;  // resident weight slab: 128 columns x 512 reduction elements
+constexpr int DR_TABLE_BYTES = DR_TILE_R * 16;
+
+__host__ __device__ constexpr int dr_stages(bool resident) { return resident ? 4 : 6; }
+__host__ __device__ constexpr int dr_stage_bytes(bool resident) { return resident ? OP_BYTES : 2 * OP_BYTES; }
+__host__ __device__ constexpr int dr_off_ring(bool resident) { return resident ? DR_SLAB_BYTES : 0; }
+__host__ __device__ constexpr int dr_off_table(bool resident) {
+    return dr_off_ring(resident) + dr_stages(resident) * dr_stage_bytes(resident);
+}
+__host__ __device__ constexpr int dr_off_bars(bool resident) { return dr_off_table(resident) + 2 * DR_TABLE_BYTES; }
+__host__ __device__ constexpr int dr_smem_bytes(bool resident) { return dr_off_bars(resident) + 256 + 1024; }
+static_assert(dr_smem_bytes(true) <= 232448 && dr_smem_bytes(false) <= 232448, "shared memory budget");
+
+struct DxRedParams {
+    int M, H, Hp;                // pixel rows of this pass, hidden width, padded hidden width
+    int n_tiles, r_tiles, k_blocks;
+    int P, b0;                   // pixel rows per image; index of the pass's first image in img / hz / S
+    const float* grid;           // (P, 2)
+    const float* img;            // (B, 4) cos, sin, dx0, dx1
+    const float* coord_w;        // (H, 2)
+    const float* hz;             // (B, Hp)  W_z z + b_c
+    float* S;                    // (B, 3, Hp)
+};
+
+template <int ACT>
+__device__ __forceinline__ void moment_elem(float v, const float4 t, float wc0, float wc1, float hzb, float& s,
+                                            float& m0, float& m1) {
+    const float h = act_const<ACT>(fmaf(wc0, t.x, fmaf(wc1, t.y, hzb)));
+    const float d = v * act_deriv_const<ACT>(h);
+    s += d;
+    m0 = fmaf(t.z, d, m0);
+    m1 = fmaf(t.w, d, m1);
+}
+
+template <int ACT, bool RESIDENT>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD, const DxRedParams p) {
+    constexpr int STAGES = dr_stages(RESIDENT);
+    constexpr int STAGE_BYTES = dr_stage_bytes(RESIDENT);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* slab = smem;                                            // RESIDENT only
+    uint8_t* ring = smem + dr_off_ring(RESIDENT);
+    float4* table = reinterpret_cast<float4*>(smem + dr_off_table(RESIDENT));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + dr_off_bars(RESIDENT));
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], slab_full, then the tmem base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader_cta = (cta_rank == 0);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+    const uint32_t slabfull = smem_u32(bars + 2 * STAGES + 4);
+    const uint32_t full0_leader = map_to_cta(full0, 0), tempty0_leader = map_to_cta(tempty0, 0);
+    const uint32_t slabfull_leader = map_to_cta(slabfull, 0);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmD);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * EPI_WARPS); }
+        mbar_init(slabfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.n_tiles * p.r_tiles;
+    const int first_tile = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: the weight slab once (RESIDENT), then the delta rows (and weight blocks) per K block =====
+        if (RESIDENT && first_tile < num_tiles) {
+            const int n0 = (first_tile % p.n_tiles) * DR_TILE_N + (int)cta_rank * 128;
+            if (is_leader_cta) mbar_expect_tx(slabfull, 2 * p.k_blocks * OP_BYTES);
+            for (int kb = 0; kb < p.k_blocks; ++kb)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    tma_load_2d_pair(smem_u32(slab + kb * OP_BYTES + i * BOX_BYTES), &tmW, slabfull_leader, n0 + i * 64,
+                                     kb * KB);
+        }
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+            const int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
+            const int n0 = nt * DR_TILE_N + (int)cta_rank * 128;
+            const int r0 = rt * DR_TILE_R + (int)cta_rank * 128;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t fb = full0_leader + 8 * stage;
+                if (is_leader_cta) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
+                uint8_t* st = ring + stage * STAGE_BYTES;
+                if (!RESIDENT) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        tma_load_2d_pair(smem_u32(st + OP_BYTES + i * BOX_BYTES), &tmW, fb, n0 + i * 64, kb * KB);
+                }
+                tma_load_2d_pair(smem_u32(st), &tmD, fb, kb * KB, r0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && is_leader_cta) {
+        // ===== MMA issuer: D[n, row] (+)= W[j, n]^T (MN-major A) x delta[row, j] (K-major B) =====
+        constexpr uint32_t idesc = make_idesc(1, 0, DR_TILE_N, DR_TILE_R);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        if (RESIDENT && first_tile < num_tiles) { mbar_wait(slabfull, 0); tc_fence_after(); }
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * DR_TILE_R;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(ring + stage * STAGE_BYTES);
+                const uint32_t sa = RESIDENT ? smem_u32(slab + kb * OP_BYTES) : sb + OP_BYTES;
+#pragma unroll
+                for (int k = 0; k < KB / 16; ++k) {
+                    const uint64_t ad = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024);
+                    const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+                    umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit_pair(empty0 + 8 * stage);
+                if (kb == p.k_blocks - 1) umma_commit_pair(tfull0 + 8 * acc);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = one hidden column n (TMEM lane), 128 of the tile's 256 pixel rows (TMEM columns) =====
+        const int q = warp & 3;                        // TMEM lane quadrant
+        const int ch = (warp - 4) >> 2;                // which half of the tile's rows
+        const int etid = threadIdx.x - 128;            // 0..255
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t tile_it = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++tile_it) {
+            const int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
+            const int n = nt * DR_TILE_N + (int)cta_rank * 128 + q * 32 + lane;
+            const bool n_ok = n < p.Hp;
+            float4* tab = table + (tile_it & 1) * DR_TILE_R;
+            {   // row table: transformed coordinate (x', y') and raw grid coordinate (c0, c1) of every row of the tile
+                const int row = rt * DR_TILE_R + etid;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) {
+                    const int bl = row / p.P, pp = row - bl * p.P;
+                    const float g0 = __ldg(p.grid + 2 * pp), g1 = __ldg(p.grid + 2 * pp + 1);
+                    const float* im = p.img + (size_t)(p.b0 + bl) * 4;
+                    const float cs = __ldg(im), sn = __ldg(im + 1);
+                    t.x = g0 * cs - g1 * sn + __ldg(im + 2);
+                    t.y = g0 * sn + g1 * cs + __ldg(im + 3);
+                    t.z = g0; t.w = g1;
+                }
+                tab[etid] = t;
+            }
+            const float wc0 = (n < p.H) ? __ldg(p.coord_w + 2 * n) : 0.f;
+            const float wc1 = (n < p.H) ? __ldg(p.coord_w + 2 * n + 1) : 0.f;
+            const int R0 = rt * DR_TILE_R + ch * 128;                  // first pixel row of this thread's columns
+            int b_cur = (R0 < p.M ? R0 : p.M - 1) / p.P;
+            int next_b = (b_cur + 1) * p.P;                            // row at which the next image starts
+            if (next_b >= p.M) next_b = 0x7fffffff;
+            float hzb = (n < p.H) ? __ldg(p.hz + (size_t)(p.b0 + b_cur) * p.Hp + n) : 0.f;
+            float s = 0.f, m0 = 0.f, m1 = 0.f;
+            auto flush = [&]() {
+                if (n_ok) {
+                    float* sp = p.S + (size_t)(p.b0 + b_cur) * 3 * p.Hp + n;
+                    atomicAdd(sp, s); atomicAdd(sp + p.Hp, m0); atomicAdd(sp + 2 * p.Hp, m1);
+                }
+                s = m0 = m1 = 0.f;
+            };
+            auto advance = [&]() {
+                flush();
+                ++b_cur;
+                next_b = (b_cur + 1) * p.P;
+                if (next_b >= p.M) next_b = 0x7fffffff;
+                hzb = (n < p.H) ? __ldg(p.hz + (size_t)(p.b0 + b_cur) * p.Hp + n) : 0.f;
+            };
+            epi_bar_sync_all(32 * EPI_WARPS);                          // the table is complete
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            if (R0 < p.M) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * DR_TILE_R + ch * 128;
+                const float4* trow = tab + ch * 128;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int rc = R0 + 32 * c;
+                    if (rc >= p.M) break;
+                    uint32_t v[32];
+                    tmem_ld32(t_row + 32 * c, v);
+                    while (next_b <= rc) advance();
+                    tmem_ld_wait();
+                    if (next_b >= rc + 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            moment_elem<ACT>(__uint_as_float(v[j]), trow[32 * c + j], wc0, wc1, hzb, s, m0, m1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (rc + j == next_b) advance();
+                            moment_elem<ACT>(__uint_as_float(v[j]), trow[32 * c + j], wc0, wc1, hzb, s, m0, m1);
+                        }
+                    }
+                }
+                flush();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+template <int ACT, bool RESIDENT>
+int launch_dx_red(const CUtensorMap& w, const CUtensorMap& d, const DxRedParams& p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = dx_red_kernel<ACT, RESIDENT>;
+    if (!configured) {
+        SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dr_smem_bytes(RESIDENT)));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(BW_THREADS);
+    cfg.dynamicSmemBytes = dr_smem_bytes(RESIDENT);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    SVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, w, d, p));
+    return SVAE_OK;
+}
+
+template <bool RESIDENT>
+int launch_dx_red_act(int act, const CUtensorMap& w, const CUtensorMap& d, const DxRedParams& p, int grid,
+                      cudaStream_t st) {
+    switch (act) {
+        case SVAE_ACT_TANH: return launch_dx_red<SVAE_ACT_TANH, RESIDENT>(w, d, p, grid, st);
+        case SVAE_ACT_LEAKYRELU: return launch_dx_red<SVAE_ACT_LEAKYRELU, RESIDENT>(w, d, p, grid, st);
+        case SVAE_ACT_RELU: return launch_dx_red<SVAE_ACT_RELU, RESIDENT>(w, d, p, grid, st);
+        case SVAE_ACT_SIGMOID: return launch_dx_red<SVAE_ACT_SIGMOID, RESIDENT>(w, d, p, grid, st);
+        default: set_error("tc_dx_moments: unknown activation %d", act); return SVAE_EINVAL;
+    }
+}
+
+}  // namespace
+
+int tc_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int act,
+                  const TcMoments& r, cudaStream_t st) {
+    if (rows <= 0) return SVAE_OK;
+    SVAE_REQUIRE(Hp % 64 == 0 && H <= Hp, SVAE_EINVAL, "tc_dx_moments: the padded width must be a multiple of 64");
+    SVAE_REQUIRE(r.grid && r.img && r.coord_w && r.hz && r.S && r.P > 0, SVAE_EINVAL, "tc_dx_moments: null argument");
+    DxRedParams p{};
+    p.M = rows; p.H = H; p.Hp = Hp;
+    p.n_tiles = ceil_div(Hp, DR_TILE_N);
+    p.r_tiles = ceil_div(rows, DR_TILE_R);
+    p.k_blocks = Hp / KB;
+    p.P = r.P; p.b0 = r.b0; p.grid = r.grid; p.img = r.img; p.coord_w = r.coord_w; p.hz = r.hz; p.S = r.S;
+    CUtensorMap mw, md;
+    SVAE_TRY(make_map(&mw, W, Hp, Hp, ldw, 64, 64));            // W[j, n]: boxes of 64 n x 64 j
+    SVAE_TRY(make_map(&md, delta, rows, Hp, ldd, 64, 128));     // delta[row, j]: boxes of 64 j x 128 rows
+    const int tiles = p.n_tiles * p.r_tiles;
+    int pairs = sm_count() / 2;
+    if (pairs > tiles) pairs = tiles;
+    // the weight slab stays in shared memory when it fits and every CTA pair keeps one column tile for its lifetime
+    bool resident = p.k_blocks * OP_BYTES <= DR_SLAB_BYTES;
+    if (resident && pairs % p.n_tiles != 0) {
+        if (pairs > p.n_tiles) pairs -= pairs % p.n_tiles; else resident = false;
+    }
+    if (resident) return launch_dx_red_act<true>(act, mw, md, p, 2 * pairs, st);
+    return launch_dx_red_act<false>(act, mw, md, p, 2 * pairs, st);
+}
+
+}  // namespace svae

@@ -551,3 +551,16 @@ def gemm_bf16(mode: int, A: torch.Tensor, W: torch.Tensor, *, M: int, N: int, K:
                                  _ptr(aux), aux.stride(0) if aux is not None else 0, activation, out.data_ptr(),
                                  out.stride(0), _stream()), "svae_gemm_bf16")
     return out
+
+
+def gemm_dx_moments(delta: torch.Tensor, W: torch.Tensor, *, H: int, grid: torch.Tensor, img: torch.Tensor,
+                    coord_w: torch.Tensor, hz: torch.Tensor, P: int, activation: int = L.ACT_TANH) -> torch.Tensor:
+    """Raw access to the fused tail of the decoder backward (tests): per-image column moments S (B, 3, Hp) of
+    (delta W) .* act'(h_0) with h_0 recomputed from (grid, img, coord_w, hz); delta (rows, Hp) and W (Hp, Hp) bf16."""
+    _require_cuda(delta, W, grid, img, coord_w, hz)
+    rows, Hp = delta.shape
+    S = torch.zeros(img.shape[0], 3, Hp, dtype=torch.float32, device=delta.device)
+    L.check(L.lib.svae_gemm_dx_moments(rows, H, Hp, delta.data_ptr(), delta.stride(0), W.data_ptr(), W.stride(0),
+                                       activation, grid.data_ptr(), img.data_ptr(), coord_w.data_ptr(), hz.data_ptr(),
+                                       S.data_ptr(), P, _stream()), "svae_gemm_dx_moments")
+    return S

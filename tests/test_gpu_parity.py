@@ -257,6 +257,47 @@ def test_tc_gemm_dw(M, N, K, ld):
     assert err < 2e-3 * max(1.0, float(ref.abs().max())), err
 
 
+# rows = B * P; (B, P, H, Hp): several images per 256-row tile, images spanning tiles, ragged last tile, padded width
+@pytest.mark.parametrize("B,P,H,Hp,act", [(3, 300, 500, 512, 0), (40, 16, 60, 64, 0), (2, 784, 500, 512, 1),
+                                          (5, 100, 1000, 1024, 0), (7, 37, 130, 192, 3)])
+def test_tc_dx_moments(B, P, H, Hp, act):
+    """Transposed dX GEMM with h_0 recomputed and delta_0 reduced per image in the epilogue (tc_bwd.cu) against
+    plain fp32 torch: S[b, {1, c0, c1}, n] = sum_p ((delta W) .* act'(h_0))[b, p, n] {1, grid[p]}."""
+    dev = _cuda()
+    SF = _sf()
+    g = torch.Generator().manual_seed(B * 1000 + P)
+    rows = B * P
+    delta = torch.zeros(rows, Hp, dtype=torch.bfloat16)
+    delta[:, :H] = (torch.randn(rows, H, generator=g) * 0.1).bfloat16()
+    W = torch.zeros(Hp, Hp, dtype=torch.bfloat16)
+    W[:H, :H] = (torch.randn(H, H, generator=g) / math.sqrt(H)).bfloat16()
+    grid = torch.rand(P, 2, generator=g) * 2 - 1
+    theta = torch.randn(B, generator=g)
+    img = torch.stack([torch.cos(theta), torch.sin(theta), 0.1 * torch.randn(B, generator=g),
+                       0.1 * torch.randn(B, generator=g)], 1).contiguous()
+    coord_w = torch.randn(H, 2, generator=g)
+    hz = torch.full((B, Hp), float("nan"))
+    hz[:, :H] = torch.randn(B, H, generator=g)
+    S = SF.gemm_dx_moments(delta.to(dev), W.to(dev), H=H, grid=grid.to(dev), img=img.to(dev), coord_w=coord_w.to(dev),
+                           hz=hz.to(dev), P=P, activation=act)
+    xp = grid[None, :, 0] * img[:, None, 0] - grid[None, :, 1] * img[:, None, 1] + img[:, None, 2]
+    yp = grid[None, :, 0] * img[:, None, 1] + grid[None, :, 1] * img[:, None, 0] + img[:, None, 3]
+    a0 = xp[..., None] * coord_w[:, 0] + yp[..., None] * coord_w[:, 1] + hz[:, None, :H]
+    if act == 0:
+        h0 = torch.tanh(a0); dact = 1 - h0 * h0
+    elif act == 1:
+        dact = torch.where(a0 > 0, 1.0, 0.01)
+    else:
+        h0 = torch.sigmoid(a0); dact = h0 * (1 - h0)
+    d0 = (delta.float() @ W.float())[:, :H].view(B, P, H) * dact
+    ref = torch.stack([d0.sum(1), (d0 * grid[None, :, 0, None]).sum(1), (d0 * grid[None, :, 1, None]).sum(1)], 1)
+    torch.cuda.synchronize()
+    got = S.cpu()[:, :, :H]
+    err = float((got - ref).abs().max())
+    assert err < 3e-3 * max(1.0, float(ref.abs().max())), err
+    assert torch.isfinite(S.cpu()[:, :, :H]).all()
+
+
 # ---- module-level API (spatial_vae.models) --------------------------------------------------------
 def _modules_from_golden(d, dev, C=1):
     import spatial_vae.models as M
