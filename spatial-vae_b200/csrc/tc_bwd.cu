@@ -33,7 +33,7 @@ constexpr int BW_THREADS = 128 + 32 * EPI_WARPS;
 constexpr int DR_TILE_N = 256;               // hidden columns per CTA-pair tile (MMA M; 128 TMEM lanes per CTA)
 constexpr int DR_TILE_R = 256;               // pixel rows per tile (MMA N; each CTA stages 128 of them)
 constexpr int DR_SLAB_BYTES = 8 * OP_BYTES;  // resident weight slab: 128 columns x 512 reduction elements
-constexpr int DR_TABLE_BYTES = DR_TILE_R * 16;
+constexpr int DR_TABLE_BYTES = DR_TILE_R * 8;      // per row pair: (g0, g0') and (g1, g1') as two float2 arrays
 
 __host__ __device__ constexpr int dr_stages(bool resident) { return resident ? 4 : 6; }
 __host__ __device__ constexpr int dr_stage_bytes(bool resident) { return resident ? OP_BYTES : 2 * OP_BYTES; }
@@ -48,6 +48,8 @@ static_assert(dr_smem_bytes(true) <= 232448 && dr_smem_bytes(false) <= 232448, "
 struct DxRedParams {
     int M, H, Hp;                // pixel rows of this pass, hidden width, padded hidden width
     int n_tiles, r_tiles, k_blocks;
+    int n_groups;                // CTA pairs per column tile: pair i owns column tile i % n_tiles and a contiguous
+                                 // range of row tiles, so its running per-image sums are flushed once per image
     int P, b0;                   // pixel rows per image; index of the pass's first image in img / hz / S
     const float* grid;           // (P, 2)
     const float* img;            // (B, 4) cos, sin, dx0, dx1
@@ -56,14 +58,37 @@ struct DxRedParams {
     float* S;                    // (B, 3, Hp)
 };
 
+// Per-thread state of the moment epilogue: hidden column n of image b_cur.  The first-layer pre-activation is affine
+// in the raw grid coordinate, a = A g0 + B g1 + C with A = Wc0 cos + Wc1 sin, B = Wc1 cos - Wc0 sin,
+// C = Wc0 dx0 + Wc1 dx1 + hz[b, n]  (train_mnist.py:50-59,70-74 folded into models.py:104), so the row table only
+// holds the grid.  Two rows are processed per packed (f32x2) instruction.
+struct MomentState {
+    float2 A, B, C;              // splats
+    float2 s, m0, m1;            // running sums of the even / odd row of each pair
+};
+
 template <int ACT>
-__device__ __forceinline__ void moment_elem(float v, const float4 t, float wc0, float wc1, float hzb, float& s,
-                                            float& m0, float& m1) {
-    const float h = act_const<ACT>(fmaf(wc0, t.x, fmaf(wc1, t.y, hzb)));
+__device__ __forceinline__ void moment_pair(float2 v, float2 gx, float2 gy, MomentState& st) {
+    const float2 a = __ffma2_rn(st.A, gx, __ffma2_rn(st.B, gy, st.C));
+    float2 h, g;
+    h.x = act_const<ACT>(a.x); h.y = act_const<ACT>(a.y);
+    if (ACT == SVAE_ACT_TANH) {
+        g = __ffma2_rn(make_float2(-h.x, -h.y), h, make_float2(1.f, 1.f));
+    } else {
+        g.x = act_deriv_const<ACT>(h.x); g.y = act_deriv_const<ACT>(h.y);
+    }
+    const float2 d = __fmul2_rn(v, g);
+    st.s = __fadd2_rn(st.s, d);
+    st.m0 = __ffma2_rn(gx, d, st.m0);
+    st.m1 = __ffma2_rn(gy, d, st.m1);
+}
+template <int ACT>
+__device__ __forceinline__ void moment_one(float v, float gx, float gy, MomentState& st) {
+    const float h = act_const<ACT>(fmaf(st.A.x, gx, fmaf(st.B.x, gy, st.C.x)));
     const float d = v * act_deriv_const<ACT>(h);
-    s += d;
-    m0 = fmaf(t.z, d, m0);
-    m1 = fmaf(t.w, d, m1);
+    st.s.x += d;
+    st.m0.x = fmaf(gx, d, st.m0.x);
+    st.m1.x = fmaf(gy, d, st.m1.x);
 }
 
 template <int ACT, bool RESIDENT>
@@ -72,10 +97,11 @@ dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
     constexpr int STAGES = dr_stages(RESIDENT);
     constexpr int STAGE_BYTES = dr_stage_bytes(RESIDENT);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // pointer arithmetic (not an integer round trip) keeps the shared state space: LDS / STS instead of generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* slab = smem;                                            // RESIDENT only
     uint8_t* ring = smem + dr_off_ring(RESIDENT);
-    float4* table = reinterpret_cast<float4*>(smem + dr_off_table(RESIDENT));
+    float2* table = reinterpret_cast<float2*>(smem + dr_off_table(RESIDENT));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + dr_off_bars(RESIDENT));
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], slab_full, then the tmem base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
@@ -105,13 +131,15 @@ dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.n_tiles * p.r_tiles;
-    const int first_tile = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+    // this pair's work: column tile nt, row tiles [rt0, rt1)
+    const int pair = blockIdx.x / 2;
+    const int nt = pair % p.n_tiles, grp = pair / p.n_tiles;
+    const int rt0 = (int)((long)grp * p.r_tiles / p.n_groups), rt1 = (int)((long)(grp + 1) * p.r_tiles / p.n_groups);
+    const int n0 = nt * DR_TILE_N + (int)cta_rank * 128;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: the weight slab once (RESIDENT), then the delta rows (and weight blocks) per K block =====
-        if (RESIDENT && first_tile < num_tiles) {
-            const int n0 = (first_tile % p.n_tiles) * DR_TILE_N + (int)cta_rank * 128;
+        if (RESIDENT && rt0 < rt1) {
             if (is_leader_cta) mbar_expect_tx(slabfull, 2 * p.k_blocks * OP_BYTES);
             for (int kb = 0; kb < p.k_blocks; ++kb)
 #pragma unroll
@@ -120,9 +148,7 @@ dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                                      kb * KB);
         }
         int stage = 0; uint32_t phase = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-            const int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-            const int n0 = nt * DR_TILE_N + (int)cta_rank * 128;
+        for (int rt = rt0; rt < rt1; ++rt) {
             const int r0 = rt * DR_TILE_R + (int)cta_rank * 128;
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -143,8 +169,8 @@ dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
         constexpr uint32_t idesc = make_idesc(1, 0, DR_TILE_N, DR_TILE_R);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        if (RESIDENT && first_tile < num_tiles) { mbar_wait(slabfull, 0); tc_fence_after(); }
-        for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        if (RESIDENT && rt0 < rt1) { mbar_wait(slabfull, 0); tc_fence_after(); }
+        for (int rt = rt0; rt < rt1; ++rt) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * DR_TILE_R;
@@ -165,87 +191,93 @@ dx_red_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && rt0 < rt1) {
         // ===== epilogue: thread = one hidden column n (TMEM lane), 128 of the tile's 256 pixel rows (TMEM columns) =====
         const int q = warp & 3;                        // TMEM lane quadrant
         const int ch = (warp - 4) >> 2;                // which half of the tile's rows
         const int etid = threadIdx.x - 128;            // 0..255
+        const int n = n0 + q * 32 + lane;
+        const bool n_ok = n < p.Hp, n_live = n < p.H;
+        const float wc0 = n_live ? __ldg(p.coord_w + 2 * n) : 0.f;
+        const float wc1 = n_live ? __ldg(p.coord_w + 2 * n + 1) : 0.f;
         int acc = 0; uint32_t acc_phase = 0;
-        uint32_t tile_it = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++tile_it) {
-            const int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-            const int n = nt * DR_TILE_N + (int)cta_rank * 128 + q * 32 + lane;
-            const bool n_ok = n < p.Hp;
-            float4* tab = table + (tile_it & 1) * DR_TILE_R;
-            {   // row table: transformed coordinate (x', y') and raw grid coordinate (c0, c1) of every row of the tile
-                const int row = rt * DR_TILE_R + etid;
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.M) {
-                    const int bl = row / p.P, pp = row - bl * p.P;
-                    const float g0 = __ldg(p.grid + 2 * pp), g1 = __ldg(p.grid + 2 * pp + 1);
-                    const float* im = p.img + (size_t)(p.b0 + bl) * 4;
-                    const float cs = __ldg(im), sn = __ldg(im + 1);
-                    t.x = g0 * cs - g1 * sn + __ldg(im + 2);
-                    t.y = g0 * sn + g1 * cs + __ldg(im + 3);
-                    t.z = g0; t.w = g1;
-                }
-                tab[etid] = t;
-            }
-            const float wc0 = (n < p.H) ? __ldg(p.coord_w + 2 * n) : 0.f;
-            const float wc1 = (n < p.H) ? __ldg(p.coord_w + 2 * n + 1) : 0.f;
-            const int R0 = rt * DR_TILE_R + ch * 128;                  // first pixel row of this thread's columns
-            int b_cur = (R0 < p.M ? R0 : p.M - 1) / p.P;
-            int next_b = (b_cur + 1) * p.P;                            // row at which the next image starts
+        MomentState ms;
+        int b_cur, next_b;                             // image of the running sums; first row of the next image
+        auto load_image = [&](int b) {
+            b_cur = b;
+            next_b = (b + 1) * p.P;
             if (next_b >= p.M) next_b = 0x7fffffff;
-            float hzb = (n < p.H) ? __ldg(p.hz + (size_t)(p.b0 + b_cur) * p.Hp + n) : 0.f;
-            float s = 0.f, m0 = 0.f, m1 = 0.f;
-            auto flush = [&]() {
-                if (n_ok) {
-                    float* sp = p.S + (size_t)(p.b0 + b_cur) * 3 * p.Hp + n;
-                    atomicAdd(sp, s); atomicAdd(sp + p.Hp, m0); atomicAdd(sp + 2 * p.Hp, m1);
-                }
-                s = m0 = m1 = 0.f;
-            };
-            auto advance = [&]() {
-                flush();
-                ++b_cur;
-                next_b = (b_cur + 1) * p.P;
-                if (next_b >= p.M) next_b = 0x7fffffff;
-                hzb = (n < p.H) ? __ldg(p.hz + (size_t)(p.b0 + b_cur) * p.Hp + n) : 0.f;
-            };
+            const float4 im = __ldg(reinterpret_cast<const float4*>(p.img) + p.b0 + b);      // cos, sin, dx0, dx1
+            const float hzb = n_live ? __ldg(p.hz + (size_t)(p.b0 + b) * p.Hp + n) : 0.f;
+            const float A = fmaf(wc0, im.x, wc1 * im.y), B = fmaf(wc1, im.x, -wc0 * im.y);
+            const float C = fmaf(wc0, im.z, fmaf(wc1, im.w, hzb));
+            ms.A = make_float2(A, A); ms.B = make_float2(B, B); ms.C = make_float2(C, C);
+            ms.s = ms.m0 = ms.m1 = make_float2(0.f, 0.f);
+        };
+        auto flush = [&]() {
+            if (n_ok) {
+                float* sp = p.S + (size_t)(p.b0 + b_cur) * 3 * p.Hp + n;
+                atomicAdd(sp, ms.s.x + ms.s.y);
+                atomicAdd(sp + p.Hp, ms.m0.x + ms.m0.y);
+                atomicAdd(sp + 2 * p.Hp, ms.m1.x + ms.m1.y);
+            }
+        };
+        {
+            const int R0 = rt0 * DR_TILE_R + ch * 128;
+            load_image((R0 < p.M ? R0 : p.M - 1) / p.P);
+        }
+        // grid coordinate of the row this thread contributes to the table of the next tile (loaded one tile ahead)
+        auto grid_of = [&](int rt) {
+            const int row = rt * DR_TILE_R + etid;
+            float2 g = make_float2(0.f, 0.f);
+            if (rt < rt1 && row < p.M) g = __ldg(reinterpret_cast<const float2*>(p.grid) + row % p.P);
+            return g;
+        };
+        float2 g_mine = grid_of(rt0);
+        uint32_t tile_it = 0;
+        for (int rt = rt0; rt < rt1; ++rt, ++tile_it) {
+            // row table, pair-interleaved: tabx[i] = (g0[2i], g0[2i+1]), taby[i] = (g1[2i], g1[2i+1])
+            float* tabf = reinterpret_cast<float*>(table + (tile_it & 1) * DR_TILE_R);
+            tabf[(etid >> 1) * 2 + (etid & 1)] = g_mine.x;
+            tabf[DR_TILE_R + (etid >> 1) * 2 + (etid & 1)] = g_mine.y;
+            g_mine = grid_of(rt + 1);
+            const float2* tabx = reinterpret_cast<const float2*>(tabf) + ch * 64;
+            const float2* taby = tabx + DR_TILE_R / 2;
+            const int R0 = rt * DR_TILE_R + ch * 128;                  // first pixel row of this thread's columns
             epi_bar_sync_all(32 * EPI_WARPS);                          // the table is complete
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             if (R0 < p.M) {
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * DR_TILE_R + ch * 128;
-                const float4* trow = tab + ch * 128;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int rc = R0 + 32 * c;
                     if (rc >= p.M) break;
                     uint32_t v[32];
                     tmem_ld32(t_row + 32 * c, v);
-                    while (next_b <= rc) advance();
+                    while (next_b <= rc) { flush(); load_image(b_cur + 1); }
                     tmem_ld_wait();
                     if (next_b >= rc + 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            moment_elem<ACT>(__uint_as_float(v[j]), trow[32 * c + j], wc0, wc1, hzb, s, m0, m1);
+                        for (int j = 0; j < 16; ++j)
+                            moment_pair<ACT>(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
+                                             tabx[16 * c + j], taby[16 * c + j], ms);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            if (rc + j == next_b) advance();
-                            moment_elem<ACT>(__uint_as_float(v[j]), trow[32 * c + j], wc0, wc1, hzb, s, m0, m1);
+                            if (rc + j == next_b) { flush(); load_image(b_cur + 1); }
+                            const float2 gx = tabx[16 * c + (j >> 1)], gy = taby[16 * c + (j >> 1)];
+                            moment_one<ACT>(__uint_as_float(v[j]), (j & 1) ? gx.y : gx.x, (j & 1) ? gy.y : gy.x, ms);
                         }
                     }
                 }
-                flush();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8 * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        flush();
     }
 
     tc_fence_before();
@@ -311,15 +343,14 @@ int tc_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const voi
     CUtensorMap mw, md;
     SVAE_TRY(make_map(&mw, W, Hp, Hp, ldw, 64, 64));            // W[j, n]: boxes of 64 n x 64 j
     SVAE_TRY(make_map(&md, delta, rows, Hp, ldd, 64, 128));     // delta[row, j]: boxes of 64 j x 128 rows
-    const int tiles = p.n_tiles * p.r_tiles;
-    int pairs = sm_count() / 2;
-    if (pairs > tiles) pairs = tiles;
-    // the weight slab stays in shared memory when it fits and every CTA pair keeps one column tile for its lifetime
-    bool resident = p.k_blocks * OP_BYTES <= DR_SLAB_BYTES;
-    if (resident && pairs % p.n_tiles != 0) {
-        if (pairs > p.n_tiles) pairs -= pairs % p.n_tiles; else resident = false;
-    }
-    if (resident) return launch_dx_red_act<true>(act, mw, md, p, 2 * pairs, st);
+    // CTA pairs = n_tiles column tiles x n_groups contiguous ranges of row tiles
+    const int max_pairs = sm_count() / 2;
+    SVAE_REQUIRE(p.n_tiles <= max_pairs, SVAE_EINVAL, "tc_dx_moments: hidden width %d too large", Hp);
+    p.n_groups = max_pairs / p.n_tiles;
+    if (p.n_groups > p.r_tiles) p.n_groups = p.r_tiles;
+    const int pairs = p.n_groups * p.n_tiles;
+    // the weight slab of the pair's column tile stays in shared memory when it fits
+    if (p.k_blocks * OP_BYTES <= DR_SLAB_BYTES) return launch_dx_red_act<true>(act, mw, md, p, 2 * pairs, st);
     return launch_dx_red_act<false>(act, mw, md, p, 2 * pairs, st);
 }
 

@@ -101,7 +101,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles (same offset in both CTAs of a pair)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared state space (LDS/STS, not generic LD/ST)
     if (align_slack(CG, LM) == 0 && smem != smem_raw) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;

@@ -265,6 +265,9 @@ def test_tc_dx_moments(B, P, H, Hp, act):
     plain fp32 torch: S[b, {1, c0, c1}, n] = sum_p ((delta W) .* act'(h_0))[b, p, n] {1, grid[p]}."""
     dev = _cuda()
     SF = _sf()
+    from spatial_vae import _lib as L
+    if L.lib.svae_device_sm_count() < 2 * ((Hp + 255) // 256):
+        pytest.skip("one CTA pair per 256-column tile is the kernel's minimum (small emulated devices)")
     g = torch.Generator().manual_seed(B * 1000 + P)
     rows = B * P
     delta = torch.zeros(rows, Hp, dtype=torch.bfloat16)
