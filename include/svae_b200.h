@@ -229,6 +229,17 @@ int  svae_gemm_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, c
                           const float* grid, const float* img, const float* coord_w, const float* hz, float* S, int P,
                           void* stream);
 
+/* Fused head of the decoder backward (loss.backward() through the output Linear and the top hidden Linear,
+ * models.py:82-85): delta (rows, Hp) = (g_o (rows, C) * out_w (C, H)) .* act'(h_top) is built on the fly from h_top
+ * (rows, Hp bf16) inside the weight-gradient GEMM  dW (H, H) += delta^T h_prev,  which also accumulates
+ * d_out_w (C, H) += g_o^T h_top, d_out_b (C) += colsum(g_o), d_b (H) += colsum(delta) (d_b may be NULL) and writes delta
+ * to delta_out (rows, Hp bf16; may be NULL).  All accumulations are fp32 atomics (+=, order not deterministic).
+ * C = 1..3; g_o is copied in 16-byte units: it must be 16-byte aligned and readable up to the next 16-byte boundary
+ * past its last element.  Building block of svae_step, exposed for tests. */
+int  svae_gemm_dw_top(int rows, int H, int Hp, const void* h_top, const void* h_prev, int activation, const float* g_o,
+                      int C, const float* out_w, float* d_out_w, float* d_out_b, float* d_b, float* dW, void* delta_out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

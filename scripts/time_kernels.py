@@ -28,6 +28,10 @@ calls = {
     "dw": lambda: SF.gemm_bf16(2, D, A, M=H, N=H, K=rows, out=dW),
     "dx_moments": lambda: SF.gemm_dx_moments(D[:B * P], W, H=H, grid=grid, img=img, coord_w=cw, hz=hz, P=P),
 }
+g_o = torch.randn(rows, 1, device=dev) * 0.1
+out_w = torch.randn(1, H, device=dev) / math.sqrt(H)
+calls["dw_top"] = lambda: SF.gemm_dw_top(A, D, g_o, out_w, H=H)
+calls["dw_top_nostore"] = lambda: SF.gemm_dw_top(A, D, g_o, out_w, H=H, want_delta=False)
 for extra in getattr(SF, "EXTRA_TIMED_KERNELS", []):
     calls.update(extra(locals()))
 alg = 2.0 * rows * H * H

@@ -421,7 +421,7 @@ int hidden_forward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Svae
 }
 
 // red: (FAST only) delta_prev is not stored: the transposed dX GEMM reduces it per image into S (tc_bwd.cu)
-struct RedSpec { TcMoments m; bool on = false; };
+struct RedSpec { TcMoments m; bool on = false; bool top = false; };
 template <typename T>
 static int hidden_backward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l, int rows,
                            const T* delta, T* delta_prev, const RedSpec& red);
@@ -456,7 +456,16 @@ int hidden_backward<__nv_bfloat16>(const DecoderCtx<__nv_bfloat16>& d, const Sva
     const int H = d.s->H, Hp = d.p->Hp;
     (void)dp;
     // dW_l (H,H; ld H) += delta^T act[l-1]   (fp32 accumulate, atomics across row splits)
-    SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
+    if (red.top) {
+        // top layer: delta is built from act[l] and g_o inside the GEMM and written to `delta` for the dX pass below
+        TcTop t;
+        t.g_o = d.g_logits(); t.C = d.s->C; t.out_w = dp.out_w;
+        t.d_out_w = g.out_w; t.d_out_b = g.out_b; t.d_b = g.hidden_b[l - 1];
+        SVAE_TRY(tc_dw_top(rows, H, Hp, d.act(l), d.act(l - 1), d.c->activation, t, g.hidden_w[l - 1], H,
+                           const_cast<__nv_bfloat16*>(delta), d.st));
+    } else {
+        SVAE_TRY(tc_gemm(2, H, H, rows, delta, Hp, d.act(l - 1), Hp, nullptr, 0, nullptr, 0, -1, g.hidden_w[l - 1], H, d.st));
+    }
     if (red.on) return tc_dx_moments(rows, H, Hp, delta, Hp, d.wbf_dx(l - 1), Hp, d.c->activation, red.m, d.st);
     return tc_gemm(1, rows, Hp, Hp, delta, Hp, d.wbf_dx(l - 1), Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation,
                    delta_prev, Hp, d.st);
@@ -494,8 +503,12 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
     const int Hp = d.p->Hp, rows = nb * s.P;
     if (rows == 0) return SVAE_OK;
     int cur = 0;
-    SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.g_logits(), rows, s.H, Hp, s.C, d.c->activation, dp.out_w, d.delta(cur),
-                             g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
+    // FAST: delta_{L-1} = (g_o W_o) .* act'(h_{L-1}) is produced inside the top layer's dW GEMM (tc_bwd.cu), which
+    // also accumulates dW_o, db_o, db_{L-1} and writes delta_{L-1} once for the dX GEMM: no separate pass
+    const bool fuse_top = !std::is_same<T, float>::value && s.L >= 2 && s.C <= 3;
+    if (!fuse_top)
+        SVAE_TRY(out_backward<T>(d.act(s.L - 1), d.g_logits(), rows, s.H, Hp, s.C, d.c->activation, dp.out_w,
+                                 d.delta(cur), g.out_w, g.out_b, s.L >= 2 ? g.hidden_b[s.L - 2] : nullptr, d.st));
     // The dX GEMM of the first hidden layer does not store delta_0: it recomputes h_0 and reduces delta_0 per image
     // into S in its epilogue (tc_bwd.cu).  Explicit coordinates, coordinate gradients and the first-layer options
     // keep the stored delta_0 and the separate reductions.
@@ -509,6 +522,7 @@ static int decoder_chunk_backward(const DecoderCtx<T>& d, const SvaeDecoderParam
             red.m.grid = grid; red.m.img = d.f(d.p->img); red.m.coord_w = dp.coord_w; red.m.hz = d.f(d.p->hz);
             red.m.S = d.f(d.p->S); red.m.P = s.P; red.m.b0 = b0;
         }
+        red.top = fuse_top && l == s.L - 1;
         SVAE_TRY(hidden_backward<T>(d, dp, g, l, rows, d.delta(cur), d.delta(cur ^ 1), red));
         cur ^= 1;
         if (l - 1 >= 1) SVAE_TRY(col_sum<T>(d.delta(cur), rows, s.H, Hp, g.hidden_b[l - 2], d.st));
@@ -977,6 +991,15 @@ int svae_gemm_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, co
     TcMoments m;
     m.grid = grid; m.img = img; m.coord_w = coord_w; m.hz = hz; m.S = S; m.P = P; m.b0 = 0;
     return tc_dx_moments(rows, H, Hp, delta, ldd, W, ldw, activation, m, (cudaStream_t)stream);
+}
+
+int svae_gemm_dw_top(int rows, int H, int Hp, const void* h_top, const void* h_prev, int activation, const float* g_o,
+                     int C, const float* out_w, float* d_out_w, float* d_out_b, float* d_b, float* dW, void* delta_out,
+                     void* stream) {
+    SVAE_REQUIRE(h_top && h_prev && g_o && out_w && d_out_w && d_out_b && dW, SVAE_EINVAL, "null argument");
+    TcTop t;
+    t.g_o = g_o; t.C = C; t.out_w = out_w; t.d_out_w = d_out_w; t.d_out_b = d_out_b; t.d_b = d_b;
+    return tc_dw_top(rows, H, Hp, h_top, h_prev, activation, t, dW, H, delta_out, (cudaStream_t)stream);
 }
 
 int svae_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,

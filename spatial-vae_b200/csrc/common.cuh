@@ -132,4 +132,17 @@ struct TcMoments {
 int tc_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int act,
                   const TcMoments& r, cudaStream_t st);
 
+
+// Top hidden layer (tc_bwd.cu): dW (H x H fp32, ld ldo) += delta^T h_prev with
+// delta[row, m] = (sum_c g_o[row, c] out_w[c, m]) * act'(h_top[row, m]) built in shared memory from h_top; also
+// d_out_w (C, H) += g_o^T h_top, d_out_b (C) += colsum g_o, d_b (H) += colsum delta (d_b may be NULL), and delta is
+// written to delta_out (rows x Hp bf16) unless that is NULL.  h_top, h_prev: rows x Hp bf16, ld Hp.
+struct TcTop {
+    const float* g_o = nullptr; int C = 0;
+    const float* out_w = nullptr;
+    float* d_out_w = nullptr; float* d_out_b = nullptr; float* d_b = nullptr;
+};
+int tc_dw_top(int rows, int H, int Hp, const void* h_top, const void* h_prev, int act, const TcTop& t, float* dW, int ldo,
+              void* delta_out, cudaStream_t st);
+
 }  // namespace svae

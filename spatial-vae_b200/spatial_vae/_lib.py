@@ -26,7 +26,7 @@ EXPORTS = [
     "svae_version", "svae_last_error", "svae_launch_count", "svae_device_sm_count", "svae_workspace_bytes",
     "svae_encoder_forward", "svae_encoder_backward", "svae_decoder_forward", "svae_decoder_backward",
     "svae_step", "svae_adam_step", "svae_adam_tick", "svae_adam_step_graph", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_ctf_filter", "svae_sm_clock_probe", "svae_gemm_bf16",
-    "svae_gemm_dx_moments",
+    "svae_gemm_dx_moments", "svae_gemm_dw_top",
 ]
 
 
@@ -97,6 +97,7 @@ def declare(lib):
     lib.svae_sm_clock_probe.argtypes = [vp, vp]
     lib.svae_gemm_bf16.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]
     lib.svae_gemm_dx_moments.argtypes = [i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.svae_gemm_dw_top.argtypes = [i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if the library lacks a declared symbol
         if name not in ("svae_version", "svae_device_sm_count", "svae_launch_count"):

@@ -564,3 +564,24 @@ def gemm_dx_moments(delta: torch.Tensor, W: torch.Tensor, *, H: int, grid: torch
                                        activation, grid.data_ptr(), img.data_ptr(), coord_w.data_ptr(), hz.data_ptr(),
                                        S.data_ptr(), P, _stream()), "svae_gemm_dx_moments")
     return S
+
+
+def gemm_dw_top(h_top: torch.Tensor, h_prev: torch.Tensor, g_o: torch.Tensor, out_w: torch.Tensor, *, H: int,
+                activation: int = L.ACT_TANH, want_delta: bool = True):
+    """Raw access to the fused head of the decoder backward (tests): returns (dW, d_out_w, d_out_b, d_b, delta) for
+    delta = (g_o out_w) .* act'(h_top), dW = delta^T h_prev, d_out_w = g_o^T h_top; h_* (rows, Hp) bf16."""
+    _require_cuda(h_top, h_prev, g_o, out_w)
+    rows, Hp = h_top.shape
+    C = g_o.shape[1]
+    dev = h_top.device
+    dW = torch.zeros(H, H, device=dev)
+    d_out_w = torch.zeros(C, H, device=dev)
+    d_out_b = torch.zeros(C, device=dev)
+    d_b = torch.zeros(H, device=dev)
+    delta = torch.zeros(rows, Hp, dtype=torch.bfloat16, device=dev) if want_delta else None
+    g_pad = torch.zeros(rows * C + 4, dtype=torch.float32, device=dev)     # the kernel copies g_o in 16-byte units
+    g_pad[:rows * C] = g_o.reshape(-1)
+    L.check(L.lib.svae_gemm_dw_top(rows, H, Hp, h_top.data_ptr(), h_prev.data_ptr(), activation, g_pad.data_ptr(), C,
+                                   out_w.data_ptr(), d_out_w.data_ptr(), d_out_b.data_ptr(), d_b.data_ptr(),
+                                   dW.data_ptr(), _ptr(delta), _stream()), "svae_gemm_dw_top")
+    return dW, d_out_w, d_out_b, d_b, delta

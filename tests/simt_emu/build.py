@@ -25,7 +25,7 @@ SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu", "ingest
 TC_KERNEL = os.environ.get("SVAE_EMU_TC", "kernel") != "ref"
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
 # tensor-core kernel sources and the number of inline red.global.add.v4.f32 statements each contains
-TC_SOURCES = {"tc_gemm.cu": 1, "tc_bwd.cu": 0}
+TC_SOURCES = {"tc_gemm.cu": 1, "tc_bwd.cu": 1}
 
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)<<<(.*?)>>>\(")
 DYN_SMEM = re.compile(r"extern __shared__ (?:__align__\(\d+\) )?(\w+) (\w+)\[\];")

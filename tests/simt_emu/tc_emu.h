@@ -76,6 +76,11 @@ inline void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int 
     tma_copy_in(dst, map, c0, c1);
     mbar_complete_tx(bar, map->box_rows * map->box_cols * map->esize);
 }
+inline void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    if ((dst & 15) || (bytes & 15) || ((uintptr_t)src & 15)) { fprintf(stderr, "tc_emu: misaligned bulk copy\n"); abort(); }
+    memcpy(smem_ptr(dst), src, bytes);
+    mbar_complete_tx(bar, bytes);
+}
 inline void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
     tma_load_2d(dst, map, leader_bar, c0, c1);
 }

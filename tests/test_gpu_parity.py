@@ -301,6 +301,37 @@ def test_tc_dx_moments(B, P, H, Hp, act):
     assert torch.isfinite(S.cpu()[:, :, :H]).all()
 
 
+@pytest.mark.parametrize("rows,H,Hp,C,act", [(3000, 500, 512, 1, 0), (777, 60, 64, 2, 0), (5000, 1000, 1024, 3, 0),
+                                             (1500, 130, 192, 1, 1)])
+def test_tc_dw_top(rows, H, Hp, C, act):
+    """Top-layer weight-gradient GEMM with delta built in shared memory from h_top and g_o (tc_bwd.cu) against torch."""
+    dev = _cuda()
+    SF = _sf()
+    g = torch.Generator().manual_seed(rows + H)
+    h_top = torch.zeros(rows, Hp, dtype=torch.bfloat16)
+    h_prev = torch.zeros(rows, Hp, dtype=torch.bfloat16)
+    h_top[:, :H] = torch.tanh(torch.randn(rows, H, generator=g)).bfloat16()
+    h_prev[:, :H] = torch.tanh(torch.randn(rows, H, generator=g)).bfloat16()
+    g_o = torch.randn(rows, C, generator=g) * 0.1
+    out_w = torch.randn(C, H, generator=g) / math.sqrt(H)
+    dW, d_out_w, d_out_b, d_b, delta = SF.gemm_dw_top(h_top.to(dev), h_prev.to(dev), g_o.to(dev), out_w.to(dev), H=H,
+                                                      activation=act)
+    ht = h_top.float()[:, :H]
+    dact = 1 - ht * ht if act == 0 else torch.where(ht > 0, 1.0, 0.01)
+    d_ref = (g_o @ out_w) * dact
+    torch.cuda.synchronize()
+    dq = delta.cpu().float()[:, :H]
+    assert float((dq - d_ref).abs().max()) < 1e-2 * float(d_ref.abs().max())
+    assert float(delta.cpu().float()[:, H:].abs().max() if Hp > H else 0.0) == 0.0
+    ref_dW = dq.t() @ h_prev.float()[:, :H]            # the GEMM consumes the bf16-rounded delta
+    scale = max(1.0, float(ref_dW.abs().max()))
+    assert float((dW.cpu() - ref_dW).abs().max()) < 2e-3 * scale
+    assert float((d_b.cpu() - d_ref.sum(0)).abs().max()) < 1e-3 * max(1.0, float(d_ref.sum(0).abs().max()))
+    ref_ow = g_o.t() @ ht
+    assert float((d_out_w.cpu() - ref_ow).abs().max()) < 1e-3 * max(1.0, float(ref_ow.abs().max()))
+    assert float((d_out_b.cpu() - g_o.sum(0)).abs().max()) < 1e-3 * max(1.0, float(g_o.sum(0).abs().max()))
+
+
 # ---- module-level API (spatial_vae.models) --------------------------------------------------------
 def _modules_from_golden(d, dev, C=1):
     import spatial_vae.models as M
