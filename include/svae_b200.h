@@ -53,8 +53,12 @@ enum { SVAE_LIK_BERNOULLI = 0, SVAE_LIK_GAUSS = 1, SVAE_LIK_GAUSS_FITNOISE = 2 }
  *   PARITY  fp32 FFMA kernels everywhere (bit-for-bit comparable with the fp32 reference up to
  *           summation order);
  *   FAST    bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulation; first layer, output
- *           layer, likelihood, KL, reductions, encoder, dW accumulation and Adam stay fp32. */
-enum { SVAE_PRECISION_PARITY = 0, SVAE_PRECISION_FAST = 1 };
+ *           layer, likelihood, KL, reductions, encoder, dW accumulation and Adam stay fp32.
+ *   PARITY_TC  fp32 activations; every hidden GEMM of both networks runs on tcgen05 as ONE bf16 GEMM over three
+ *           hi/lo split terms of its operands (A_hi B_hi + A_hi B_lo + A_lo B_hi, error ~2^-16, fp32 TMEM
+ *           accumulation, accurate tanhf in the epilogue); everything else as PARITY.  Meets both parity gates
+ *           (per-image ELBO 1e-3, parameters 1e-4 after 10 Adam steps) on tensor cores. */
+enum { SVAE_PRECISION_PARITY = 0, SVAE_PRECISION_FAST = 1, SVAE_PRECISION_PARITY_TC = 2 };
 
 typedef struct {
     int32_t B;        /* images in this call (this rank's slice of the minibatch)              */
@@ -114,9 +118,16 @@ typedef struct {
     const float* y;             /* (B, P*C_target) targets; C_target = Cin                       */
     const float* y_enc;         /* (B, P*Cin) what the encoder sees; NULL = y (augmentation, train_particles.py:28-50) */
     const float* theta_offset;  /* (B) added to theta before rotating (train_particles.py:71-74); may be NULL */
-    const float* eps;           /* (B, I) the N(0,1) draw of train_mnist.py:38                   */
+    const float* eps;           /* (B, I) the N(0,1) draw of train_mnist.py:38; NULL = draw it in the kernel (rng_* below) */
     const float* ctf;           /* (B, k_ctf, k_ctf) real-space kernels or NULL                  */
     const uint8_t* mask;        /* (P) 0/1 pixel mask or NULL (train_particles.py:126-132)       */
+    /* In-kernel draw of eps (used when eps == NULL): Philox4x32-10 keyed by rng_seed, counter = (global image index,
+     * latent block, *rng_step), Box-Muller.  The value of image g of the minibatch depends only on (seed, step, g), so
+     * a data-parallel run draws the same eps however the minibatch is split across ranks (SURVEY 7.2 "RNG parity").
+     * rng_step is a DEVICE pointer so that a captured CUDA graph draws fresh numbers on every replay. */
+    const int32_t* rng_step;    /* device pointer to the step counter; required when eps == NULL  */
+    uint64_t rng_seed;
+    int64_t  rng_image_offset;  /* global minibatch index of this call's first image (this rank's slice) */
 } SvaeStepInputs;
 
 /* Outputs of one eval_minibatch (all optional except stats). */
@@ -218,6 +229,14 @@ int  svae_gemm_bf16(int mode, int M, int N, int K,
                     const void* A, int lda, const void* W, int ldw,
                     const float* bias, const void* aux, int ldaux, int activation,
                     void* out, int ldo, void* stream);
+
+/* ResidLinear.forward (reference spatial_vae/models.py:13-21): out (rows, n) = act(x W^T + b + x), W (n, n), fp32 FFMA
+ * with the skip connection in the GEMM epilogue.  The backward takes the forward's out and g_out = dLoss/dout, uses
+ * g_pre (rows, n) as scratch, ACCUMULATES g_w (n, n) and g_b (n) and writes g_x (rows, n) = g_pre W + g_pre. */
+int  svae_resid_linear_forward(const float* x, const float* w, const float* b, float* out, int rows, int n,
+                               int activation, void* stream);
+int  svae_resid_linear_backward(const float* x, const float* w, const float* out, const float* g_out, float* g_pre,
+                                float* g_x, float* g_w, float* g_b, int rows, int n, int activation, void* stream);
 
 /* Fused tail of the decoder backward (loss.backward() through SpatialGenerator.forward's first layer,
  * models.py:104-124, train_mnist.py:50-59,70-74): delta_0 = (delta (rows, Hp) * W (Hp, Hp; [j][n])) .* act'(h_0) is

@@ -33,7 +33,7 @@ struct Plan {
     size_t esize = 4;      // bytes per activation element
     size_t total = 0;
     // offsets (bytes)
-    size_t enc_acts, zo, enc_scratch, lat, img, zs, hz, S, dz, g_zo, o, g_o, acts, delta, wbf16;
+    size_t enc_acts, zo, enc_scratch, lat, eps, img, zs, hz, S, dz, g_zo, o, g_o, acts, delta, wbf16;
     size_t act_stride = 0, delta_stride = 0, w_stride = 0;
     // encoder on tensor cores (FAST): leading dimension of the fp32 activations and the bf16 split buffers
     int enc_ld = 0;
@@ -45,6 +45,9 @@ struct Plan {
     bool opt = false;
     size_t weff = 0, dlat = 0, enc_wres = 0;
     bool resid_tc = false;          // ResidLinear layers on the tensor-core GEMMs: wbf16 also holds the W + I copies
+    // PARITY_TC: bf16 split buffers of the decoder's 3-term GEMMs (K-concatenated rows x 3Hp; row-stacked 3rows x Hp)
+    bool tc3 = false;
+    size_t d_xs = 0, d_gs = 0, d_as = 0, d_wk[SVAE_MAX_LAYERS], d_wr[SVAE_MAX_LAYERS];
     long w_img_stride = 0;
     // chunk-local buffers (o, g_o, acts, delta) exist `sets` times, `set_stride` bytes apart: with two sets the
     // chunks alternate between two streams so the bandwidth-bound passes of one overlap the GEMMs of the other
@@ -97,8 +100,8 @@ static int validate(const SvaeShape& s, const SvaeConfig& c) {
     SVAE_REQUIRE(s.Z >= 0 && s.I == s.Z + (c.rotate ? 1 : 0) + (c.translate ? 2 : 0), SVAE_EINVAL,
                  "inference dim %d != z_dim %d + rotate + 2*translate", s.I, s.Z);
     SVAE_REQUIRE(c.activation >= 0 && c.activation <= 3, SVAE_EINVAL, "unknown activation %d", c.activation);
-    SVAE_REQUIRE(c.precision == SVAE_PRECISION_PARITY || c.precision == SVAE_PRECISION_FAST, SVAE_EINVAL,
-                 "unknown precision %d", c.precision);
+    SVAE_REQUIRE(c.precision == SVAE_PRECISION_PARITY || c.precision == SVAE_PRECISION_FAST ||
+                 c.precision == SVAE_PRECISION_PARITY_TC, SVAE_EINVAL, "unknown precision %d", c.precision);
     if (c.likelihood == SVAE_LIK_GAUSS_FITNOISE) {
         SVAE_REQUIRE(s.C == 2, SVAE_EINVAL, "fit-noise needs n_out == 2 (train_particles.py:447-449)");
         // the reference's variance convolution lacks groups= and crashes (train_particles.py:121-124,137)
@@ -131,10 +134,18 @@ static bool resid_on_tensor_cores() {
 static bool use_fast(const SvaeConfig& c) {
     return c.precision == SVAE_PRECISION_FAST && (!c.resid || resid_on_tensor_cores());
 }
+// PARITY_TC: fp32 activations, every hidden GEMM of BOTH networks as one bf16 tcgen05 GEMM over three hi/lo split
+// terms (error ~2^-16, fp32 accumulation); everything else as PARITY.  ResidLinear networks and the first-layer
+// options run PARITY instead (their fp32 epilogue addends have no tensor-core variant).
+static bool use_tc3(const SvaeConfig& c) {
+    return c.precision == SVAE_PRECISION_PARITY_TC && !c.resid && !c.expand_coords && !c.bilinear;
+}
 
 static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     const bool fast = use_fast(c);
-    p.Hp = fast ? (int)round_up(s.H, 64) : (int)round_up(s.H, 2);
+    const bool tc3 = use_tc3(c);
+    p.tc3 = tc3;
+    p.Hp = (fast || tc3) ? (int)round_up(s.H, 64) : (int)round_up(s.H, 2);
     p.esize = fast ? 2 : 4;
     p.F = c.expand_coords ? 5 : 2;
     p.opt = c.expand_coords || c.bilinear;
@@ -142,8 +153,8 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.w_img_stride = c.bilinear ? (long)s.H * p.F : 0;
     int chunk = c.chunk_images;
     if (chunk <= 0) {
-        // bound the activation workspace (L act + 2 delta matrices) to ~6 GiB per pass
-        const double per_image = (double)s.P * p.Hp * p.esize * (s.L + 2);
+        // bound the activation workspace (L act + 2 delta matrices, + the split buffers of PARITY_TC) to ~6 GiB per pass
+        const double per_image = (double)s.P * p.Hp * (p.esize * (s.L + 2) + (tc3 ? 18 : 0));
         chunk = (int)fmax(1.0, floor(6.0 * 1024 * 1024 * 1024 / per_image));
     }
     if (chunk > s.B) chunk = s.B;
@@ -161,12 +172,12 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     const size_t B = (size_t)(s.B > 0 ? s.B : 1), I = (size_t)s.I, rows = (size_t)chunk * s.P;
     size_t cur = 0;
     const size_t Hqp = (size_t)round_up(s.Hq, 64);
-    p.enc_ld = fast ? (int)Hqp : s.Hq;
+    p.enc_ld = (fast || tc3) ? (int)Hqp : s.Hq;
     p.enc_acts = take(cur, (size_t)s.Lq * B * p.enc_ld * 4);
     p.zo = take(cur, B * 2 * I * 4);
     const size_t wide = (size_t)((size_t)p.enc_ld > 2 * I ? (size_t)p.enc_ld : 2 * I);
     p.enc_scratch = take(cur, 2 * B * wide * 4);
-    if (fast) {
+    if (fast || tc3) {
         const size_t kp0 = (size_t)round_up((long)s.P * s.Cin, 64);
         const size_t kmax = kp0 > Hqp ? kp0 : Hqp;
         p.xs_k = take(cur, B * 3 * kmax * 2);
@@ -179,6 +190,7 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
         }
     }
     p.lat = take(cur, B * I * 4);
+    p.eps = take(cur, B * I * 4);          // the in-kernel eps draw, kept for the backward
     p.img = take(cur, B * 4 * 4);
     p.zs = take(cur, B * (size_t)(s.Z > 0 ? s.Z : 1) * 4);
     p.hz = take(cur, B * p.Hp * 4);
@@ -195,11 +207,20 @@ static int make_plan(const SvaeShape& s, const SvaeConfig& c, Plan& p) {
     p.acts = take(cur, p.act_stride * s.L);
     p.delta_stride = p.act_stride;
     p.delta = take(cur, p.delta_stride * 2);
+    if (tc3) {
+        p.d_xs = take(cur, rows * 3 * p.Hp * 2);
+        p.d_gs = take(cur, 3 * rows * p.Hp * 2);
+        p.d_as = take(cur, 3 * rows * p.Hp * 2);
+    }
     p.set_stride = cur - p.o;
     if (p.sets == 2) cur += p.set_stride;
     p.w_stride = (size_t)p.Hp * p.Hp * 2;
     // bf16 hidden weights; with resid_tc a second set with the identity added follows (operands of the dX GEMMs)
     p.wbf16 = take(cur, fast ? p.w_stride * (s.L > 1 ? s.L - 1 : 1) * (p.resid_tc ? 2 : 1) : 0);
+    for (int l = 0; l < s.L - 1; ++l) {
+        p.d_wk[l] = take(cur, tc3 ? (size_t)p.Hp * 3 * p.Hp * 2 : 0);
+        p.d_wr[l] = take(cur, tc3 ? (size_t)3 * p.Hp * p.Hp * 2 : 0);
+    }
     p.total = cur;
     return SVAE_OK;
 }
@@ -387,6 +408,7 @@ struct DecoderCtx {
     float* g_logits() const { return reinterpret_cast<float*>(ws + set_off + p->g_o); }
     float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
     __nv_bfloat16* wbf(int l) const { return reinterpret_cast<__nv_bfloat16*>(ws + p->wbf16 + p->w_stride * l); }
+    __nv_bfloat16* b16(size_t off) const { return reinterpret_cast<__nv_bfloat16*>(ws + set_off + off); }
     // operand of the dX GEMM of hidden layer l+1: W, or the W + I copy for ResidLinear layers on tensor cores
     __nv_bfloat16* wbf_dx(int l) const { return wbf(p->resid_tc ? (s->L - 1) + l : l); }
     // first-layer coordinate weights of image 0: W_eff (B, H*F) with bilinear, else coord_linear.weight
@@ -399,6 +421,16 @@ static int hidden_forward(const DecoderCtx<T>& d, const SvaeDecoderParams& dp, i
 template <>
 int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, int l, int rows, bool) {
     const int H = d.s->H, Hp = d.p->Hp;
+    if (d.p->tc3) {
+        // act[l] = act(act[l-1] W^T + b): operands split into (hi, hi, lo) x (hi, lo, hi) bf16 terms along K
+        __nv_bfloat16* xs = d.b16(d.p->d_xs);
+        __nv_bfloat16* wk = reinterpret_cast<__nv_bfloat16*>(d.ws + d.p->d_wk[l - 1]);
+        SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, xs, rows, Hp, 1, 0, d.st));
+        TcExtra f32out;
+        f32out.out_f32 = 1;
+        return tc_gemm(0, rows, Hp, 3 * Hp, xs, 3 * Hp, wk, 3 * Hp, dp.hidden_b[l - 1], H, nullptr, 0, d.c->activation,
+                       d.act(l), Hp, d.st, f32out);
+    }
     SgemmArgs a{};
     a.A = d.act(l - 1); a.sAm = Hp; a.sAk = 1;
     a.B = dp.hidden_w[l - 1]; a.sBk = 1; a.sBn = H;
@@ -429,6 +461,19 @@ template <>
 int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& dp, SvaeDecoderParams& g, int l,
                            int rows, const float* delta, float* delta_prev, const RedSpec&) {
     const int H = d.s->H, Hp = d.p->Hp;
+    if (d.p->tc3) {
+        // dW_l += delta^T act[l-1]: the three terms stacked along the reduction dimension (rows)
+        SVAE_TRY(split3(delta, rows, H, Hp, d.b16(d.p->d_gs), rows, Hp, 0, 0, d.st));
+        SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, d.b16(d.p->d_as), rows, Hp, 0, 1, d.st));
+        SVAE_TRY(tc_gemm(2, H, H, 3 * rows, d.b16(d.p->d_gs), Hp, d.b16(d.p->d_as), Hp, nullptr, 0, nullptr, 0, -1,
+                         g.hidden_w[l - 1], H, d.st));
+        // delta_prev = (delta W_l) .* act'(act[l-1])
+        SVAE_TRY(split3(delta, rows, H, Hp, d.b16(d.p->d_xs), rows, Hp, 1, 0, d.st));
+        TcExtra f32out;
+        f32out.out_f32 = 1;
+        return tc_gemm(1, rows, Hp, 3 * Hp, d.b16(d.p->d_xs), 3 * Hp, reinterpret_cast<__nv_bfloat16*>(d.ws + d.p->d_wr[l - 1]),
+                       Hp, nullptr, 0, d.act(l - 1), Hp, d.c->activation, delta_prev, Hp, d.st, f32out);
+    }
     // dW_l (H,H) += delta^T act[l-1]
     SgemmArgs w{};
     w.A = delta; w.sAm = 1; w.sAk = Hp;
@@ -551,6 +596,16 @@ static int prepare_bf16_weights(const SvaeShape& s, const Plan& p, const SvaeDec
             SVAE_TRY(to_bf16_padded(dp.hidden_w[l], s.H, s.H, wi, p.Hp, p.Hp, st));
             SVAE_TRY(add_identity_bf16(dp.hidden_w[l], s.H, wi, p.Hp, st));
         }
+    }
+    return SVAE_OK;
+}
+
+// PARITY_TC: hi/lo split terms of the hidden weights, once per call: K-concatenated for the forward GEMM
+// (Hp x 3Hp, B side), row-stacked for the dX GEMM (3Hp x Hp, B side)
+static int prepare_split_weights(const SvaeShape& s, const Plan& p, const SvaeDecoderParams& dp, char* ws, cudaStream_t st) {
+    for (int l = 0; l < s.L - 1; ++l) {
+        SVAE_TRY(split3(dp.hidden_w[l], s.H, s.H, s.H, reinterpret_cast<__nv_bfloat16*>(ws + p.d_wk[l]), p.Hp, p.Hp, 1, 1, st));
+        SVAE_TRY(split3(dp.hidden_w[l], s.H, s.H, s.H, reinterpret_cast<__nv_bfloat16*>(ws + p.d_wr[l]), p.Hp, p.Hp, 0, 1, st));
     }
     return SVAE_OK;
 }
@@ -688,14 +743,19 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     const float* x_enc = in.y_enc ? in.y_enc : in.y;
     float* zo = d.f(p.zo);
     constexpr bool kFast = !std::is_same<T, float>::value;
+    const bool enc_on_tc = kFast || p.tc3;
     EncTc enc_tc{&s, &p, ws, st};
-    if (kFast) SVAE_TRY(encoder_forward_tc(enc_tc, c.activation, qp, x_enc, zo));
+    if (enc_on_tc) SVAE_TRY(encoder_forward_tc(enc_tc, c.activation, qp, x_enc, zo));
     else SVAE_TRY(encoder_forward_impl(s, c.activation, qp, x_enc, zo, d.f(p.enc_acts), st, c.resid != 0));
     float* lat = out.latent ? out.latent : d.f(p.lat);
-    SVAE_TRY(latent_forward(s, c, zo, in.eps, in.theta_offset, lat, d.f(p.img), d.f(p.zs), out.stats, st));
+    LatentRng rng;
+    rng.step = in.rng_step; rng.seed = in.rng_seed; rng.image_offset = in.rng_image_offset;
+    const float* eps = in.eps ? in.eps : d.f(p.eps);
+    SVAE_TRY(latent_forward(s, c, zo, in.eps, in.theta_offset, lat, d.f(p.img), d.f(p.zs), out.stats, st, rng, d.f(p.eps)));
     SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
     if (c.bilinear) SVAE_TRY(bilinear_weights(s, p, dp, d.f(p.zs), d.f(p.weff), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
+    if (p.tc3) SVAE_TRY(prepare_split_weights(s, p, dp, ws, st));
     if (train && kFast) SVAE_CUDA(cudaMemsetAsync(ws + p.S, 0, (size_t)s.B * p.K1 * p.Hp * sizeof(float), st));
     AuxStream* aux = nullptr;
     if (p.sets == 2) {
@@ -726,15 +786,15 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
             SVAE_TRY(latent_coord_grad(p.F, s.B, s.H, p.Hp, d.l0_w(dp), p.w_img_stride, d.f(p.S), d.f(p.img),
                                        d.f(p.dlat), st));
             SVAE_TRY(latent_backward(s, c, nullptr, p.Hp, d.f(p.img), nullptr, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
-                                     in.eps, d.f(p.g_zo), st, d.f(p.dlat)));
+                                     eps, d.f(p.g_zo), st, d.f(p.dlat)));
         } else {
             SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
                                              s.Z > 0 ? d.f(p.dz) : nullptr, st));
             SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
-                                     in.eps, d.f(p.g_zo), st));
+                                     eps, d.f(p.g_zo), st));
         }
         if (gq) {
-            if (kFast) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));
+            if (enc_on_tc) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));
             else SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
                                                 d.f(p.enc_scratch), st, c.resid != 0));
         }
@@ -776,6 +836,7 @@ static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, 
     SVAE_TRY(latent_projection(s, p, dp, d.f(p.zs), d.f(p.hz), st));
     if (c.bilinear) SVAE_TRY(bilinear_weights(s, p, dp, d.f(p.zs), d.f(p.weff), st));
     if (!std::is_same<T, float>::value) SVAE_TRY(prepare_bf16_weights(s, p, dp, ws, st));
+    if (p.tc3) SVAE_TRY(prepare_split_weights(s, p, dp, ws, st));
     for (int b0 = 0; b0 < s.B; b0 += p.chunk) {
         const int nb = (s.B - b0 < p.chunk) ? (s.B - b0) : p.chunk;
         SVAE_TRY(decoder_chunk_forward<T>(d, dp, b0, nb, nullptr, x, y_hat));
@@ -892,7 +953,8 @@ int svae_step(const SvaeShape* shape, const SvaeConfig* cfg, const SvaeDecoderPa
               SvaeDecoderParams* dec_grads, SvaeEncoderParams* enc_grads, void* workspace, size_t workspace_bytes,
               void* stream) {
     SVAE_REQUIRE(shape && cfg && dec && enc && in && out && workspace, SVAE_EINVAL, "null argument");
-    SVAE_REQUIRE(in->grid && in->y && in->eps && out->stats, SVAE_EINVAL, "grid, y, eps and stats are required");
+    SVAE_REQUIRE(in->grid && in->y && out->stats, SVAE_EINVAL, "grid, y and stats are required");
+    SVAE_REQUIRE(in->eps || in->rng_step, SVAE_EINVAL, "eps or rng_step (in-kernel draw) is required");
     SVAE_TRY(validate(*shape, *cfg));
     SVAE_REQUIRE(shape->Lq >= 1 && shape->Lq <= SVAE_MAX_LAYERS, SVAE_EINVAL, "bad encoder depth %d", shape->Lq);
     SVAE_REQUIRE((shape->k_ctf > 0) == (in->ctf != nullptr), SVAE_EINVAL, "k_ctf and the ctf pointer disagree");
@@ -982,6 +1044,48 @@ int svae_ctf_filter(const double* params, int n_particles, int n, int m, double 
 int svae_sm_clock_probe(float* out_mhz, void* stream) {
     SVAE_REQUIRE(out_mhz != nullptr, SVAE_EINVAL, "null argument");
     return clock_probe(out_mhz, (cudaStream_t)stream);
+}
+
+int svae_resid_linear_forward(const float* x, const float* w, const float* b, float* out, int rows, int n, int activation,
+                              void* stream) {
+    SVAE_REQUIRE(x && w && b && out && rows >= 0 && n > 0, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(activation >= 0 && activation <= 3, SVAE_EINVAL, "unknown activation %d", activation);
+    if (rows == 0) return SVAE_OK;
+    SgemmArgs a{};
+    a.A = x; a.sAm = n; a.sAk = 1;
+    a.B = w; a.sBk = 1; a.sBn = n;
+    a.C = out; a.ldc = n;
+    a.M = rows; a.N = n; a.K = n;
+    a.bias = b; a.act = activation;
+    a.add = x; a.ld_add = n;                         // the skip connection rides in the GEMM epilogue
+    return sgemm(a, (cudaStream_t)stream);
+}
+
+int svae_resid_linear_backward(const float* x, const float* w, const float* out, const float* g_out, float* g_pre,
+                               float* g_x, float* g_w, float* g_b, int rows, int n, int activation, void* stream) {
+    SVAE_REQUIRE(x && w && out && g_out && g_pre && g_x && g_w && g_b && rows >= 0 && n > 0, SVAE_EINVAL, "null argument");
+    SVAE_REQUIRE(activation >= 0 && activation <= 3, SVAE_EINVAL, "unknown activation %d", activation);
+    if (rows == 0) return SVAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // g_pre = g_out .* act'(out)   (an identity "GEMM" is avoided: scale rows through the dX epilogue of K = 0)
+    SVAE_TRY(act_backward(out, g_out, g_pre, (long)rows * n, activation, st));
+    // dW (n, n) += g_pre^T x ; db += colsum g_pre
+    SgemmArgs wg{};
+    wg.A = g_pre; wg.sAm = 1; wg.sAk = n;
+    wg.B = x; wg.sBk = n; wg.sBn = 1;
+    wg.C = g_w; wg.ldc = n;
+    wg.M = n; wg.N = n; wg.K = rows;
+    wg.accumulate = 1; wg.split_k = rows >= 2048 ? 8 : (rows >= 512 ? 4 : 1);
+    SVAE_TRY(sgemm(wg, st));
+    SVAE_TRY(col_sum<float>(g_pre, rows, n, n, g_b, st));
+    // g_x = g_pre W + g_pre
+    SgemmArgs xg{};
+    xg.A = g_pre; xg.sAm = n; xg.sAk = 1;
+    xg.B = w; xg.sBk = n; xg.sBn = 1;
+    xg.C = g_x; xg.ldc = n;
+    xg.M = rows; xg.N = n; xg.K = n;
+    xg.add = g_pre; xg.ld_add = n;
+    return sgemm(xg, st);
 }
 
 int svae_gemm_dx_moments(int rows, int H, int Hp, const void* delta, int ldd, const void* W, int ldw, int activation,

@@ -8,8 +8,12 @@ namespace svae {
 // Reparameterisation + KL (train_mnist.py:33-39,62-63,84-86).  One thread per image.
 //   zo (B,2I) = [mu | logstd]; writes lat (B,I), img (B,4) = cos,sin,dx0,dx1, zs (B,Z) scaled z,
 //   stats[b*3+1] = kl_b.
+// eps == NULL: eps is drawn in the kernel (Philox4x32-10 keyed by rng.seed, counter = (global image, latent block,
+// *rng.step), Box-Muller) and written to eps_out (B,I) for the backward.
+struct LatentRng { const int32_t* step = nullptr; uint64_t seed = 0; int64_t image_offset = 0; };
 int latent_forward(const SvaeShape& s, const SvaeConfig& c, const float* zo, const float* eps,
-                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st);
+                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st,
+                   const LatentRng& rng = LatentRng(), float* eps_out = nullptr);
 
 // hz[b, n] = coord_b[n] for all b when Z == 0 (otherwise an sgemm with bias does it)
 int fill_rows(float* dst, const float* row, int rows, int n, int ld, cudaStream_t st);
@@ -85,6 +89,9 @@ template <typename T>
 int coord_row_grad_opt(int F, const T* delta0, int rows, int P, int H, int Hp, const float* w, long w_img_stride,
                        const float* x, float* g_x, cudaStream_t st);
 
+
+// g_pre[i] = g[i] * act'(out[i]) with act' expressed through the layer OUTPUT (ResidLinear.forward's backward)
+int act_backward(const float* out, const float* g, float* g_pre, long n, int act, cudaStream_t st);
 
 int adam_tick(int* t_dev, float* bias_corr_dev, float b1, float b2, cudaStream_t st);
 // bias_corr_dev: optional device pointer to {1 - b1^t, sqrt(1 - b2^t)}; when set it overrides t

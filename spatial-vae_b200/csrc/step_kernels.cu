@@ -68,10 +68,35 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // ------------------------------------------------------------------------------------------------
 // reparameterisation + KL   (train_mnist.py:33-39,62-63,84-86; particles :85-86,99)
 // ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0, k1) -> four uniform 32-bit words
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// element i of the N(0,1) row of global image g at step t: Box-Muller on the Philox block (g, i / 4, t)
+__device__ __forceinline__ float philox_normal(uint64_t seed, long g, int i, int step) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)(i >> 2), (uint32_t)step),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t a = (i & 2) ? r.z : r.x, b = (i & 2) ? r.w : r.y;
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.f / 16777216.f);          // (0, 1)
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.f / 16777216.f);
+    const float rad = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    return rad * ((i & 1) ? sn : cs);
+}
+
 __global__ void __launch_bounds__(256) latent_forward_k(SvaeShape s, SvaeConfig c, const float* __restrict__ zo,
                                                         const float* __restrict__ eps, const float* __restrict__ toff,
                                                         float* __restrict__ lat, float* __restrict__ img,
-                                                        float* __restrict__ zs, float* __restrict__ stats) {
+                                                        float* __restrict__ zs, float* __restrict__ stats,
+                                                        LatentRng rng, float* __restrict__ eps_out) {
     // one warp per image, lanes over the I latent dimensions
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= s.B) return;
@@ -80,11 +105,19 @@ __global__ void __launch_bounds__(256) latent_forward_k(SvaeShape s, SvaeConfig 
     const float* ls = mu + I;
     const int rot = c.rotate ? 1 : 0;
     const int zcol = rot + (c.translate ? 2 : 0);
+    const int step = (eps == nullptr) ? *rng.step : 0;
     float kl = 0.f;
     for (int i = lane; i < I; i += 32) {
         const float m = mu[i], l = ls[i];
         const float sd = expf(l);
-        const float v = sd * eps[(long)b * I + i] + m;
+        float e;
+        if (eps != nullptr) {
+            e = eps[(long)b * I + i];
+        } else {
+            e = philox_normal(rng.seed, rng.image_offset + b, i, step);
+            eps_out[(long)b * I + i] = e;
+        }
+        const float v = sd * e + m;
         if (lat) lat[(long)b * I + i] = v;
         if (rot && i == 0) {
             const float th = v + (toff ? toff[b] : 0.f);
@@ -108,8 +141,11 @@ __global__ void __launch_bounds__(256) latent_forward_k(SvaeShape s, SvaeConfig 
 }
 
 int latent_forward(const SvaeShape& s, const SvaeConfig& c, const float* zo, const float* eps,
-                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st) {
-    latent_forward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, zo, eps, theta_offset, lat, img, zs, stats);
+                   const float* theta_offset, float* lat, float* img, float* zs, float* stats, cudaStream_t st,
+                   const LatentRng& rng, float* eps_out) {
+    SVAE_REQUIRE(eps != nullptr || (rng.step != nullptr && eps_out != nullptr), SVAE_EINVAL,
+                 "either eps or the in-kernel generator (rng_step) is required");
+    latent_forward_k<<<ceil_div(s.B, 8), 256, 0, st>>>(s, c, zo, eps, theta_offset, lat, img, zs, stats, rng, eps_out);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
@@ -1187,6 +1223,17 @@ __global__ void split3_k(const float* __restrict__ src, int rows, int cols, long
         d[0] = hi; d[seg] = t1; d[2 * seg] = t2;
     }
 }
+__global__ void act_backward_k(const float* __restrict__ out, const float* __restrict__ g, float* __restrict__ g_pre,
+                               long n, int act) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g_pre[i] = g[i] * act_deriv_from_out(act, out[i]);
+}
+int act_backward(const float* out, const float* g, float* g_pre, long n, int act, cudaStream_t st) {
+    act_backward_k<<<ceil_div(n, 256), 256, 0, st>>>(out, g, g_pre, n, act);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
 int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, int rows_p, int cols_p, int kcat,
            int pattern, cudaStream_t st) {
     split3_k<<<ceil_div((long)rows_p * cols_p, 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat, pattern);

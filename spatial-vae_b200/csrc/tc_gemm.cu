@@ -371,7 +371,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const float x = __uint_as_float(v[4 * j + e]);
-                                    r[e] = (MODE == 0) ? act_const<ACT>(x + s_bias[tc + 4 * j + e])
+                                    // fp32 outputs are the error-compensated (3-term) GEMMs: accurate tanhf / expf here
+                                    r[e] = (MODE == 0) ? act_apply<false>(ACT, x + s_bias[tc + 4 * j + e])
                                                        : x * act_deriv_const<ACT>(af[4 * j + e]);
                                 }
                                 *reinterpret_cast<float4*>(ostage + row * 128 + ((j ^ (row & 7)) << 4)) =

@@ -16,17 +16,17 @@ MAX_LAYERS = 8
 
 ACT_TANH, ACT_LEAKYRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 LIK_BERNOULLI, LIK_GAUSS, LIK_GAUSS_FITNOISE = 0, 1, 2
-PRECISION_PARITY, PRECISION_FAST = 0, 1
+PRECISION_PARITY, PRECISION_FAST, PRECISION_PARITY_TC = 0, 1, 2
 ENC_RESID = 0x100          # OR-ed into the activation argument of svae_encoder_forward/backward
 
 ACT_CODES = {"tanh": ACT_TANH, "leakyrelu": ACT_LEAKYRELU, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
-PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST}
+PRECISION_CODES = {"parity": PRECISION_PARITY, "fast": PRECISION_FAST, "parity_tc": PRECISION_PARITY_TC}
 
 EXPORTS = [
     "svae_version", "svae_last_error", "svae_launch_count", "svae_device_sm_count", "svae_workspace_bytes",
     "svae_encoder_forward", "svae_encoder_backward", "svae_decoder_forward", "svae_decoder_backward",
     "svae_step", "svae_adam_step", "svae_adam_tick", "svae_adam_step_graph", "svae_gather_rows", "svae_rotation_matrices", "svae_rotate_bicubic", "svae_ctf_filter", "svae_sm_clock_probe", "svae_gemm_bf16",
-    "svae_gemm_dx_moments", "svae_gemm_dw_top",
+    "svae_gemm_dx_moments", "svae_gemm_dw_top", "svae_resid_linear_forward", "svae_resid_linear_backward",
 ]
 
 
@@ -54,7 +54,8 @@ class SvaeEncoderParams(C.Structure):
 
 
 class SvaeStepInputs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("grid", "y", "y_enc", "theta_offset", "eps", "ctf", "mask")]
+    _fields_ = [(n, C.c_void_p) for n in ("grid", "y", "y_enc", "theta_offset", "eps", "ctf", "mask", "rng_step")] + \
+               [("rng_seed", C.c_uint64), ("rng_image_offset", C.c_int64)]
 
 
 class SvaeStepOutputs(C.Structure):
@@ -98,6 +99,8 @@ def declare(lib):
     lib.svae_gemm_bf16.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp, i32, vp]
     lib.svae_gemm_dx_moments.argtypes = [i32, i32, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     lib.svae_gemm_dw_top.argtypes = [i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.svae_resid_linear_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.svae_resid_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if the library lacks a declared symbol
         if name not in ("svae_version", "svae_device_sm_count", "svae_launch_count"):

@@ -128,6 +128,74 @@ def random_minibatch_generator(x, y, p_net, z_dim, z_scale=1, use_cuda=False):
 
 
 # --------------------------------------------------------------------------------------------------
+# --vanilla: the non-spatial MLP generator (reference models.py:135-172, train_mnist.py:351-357).  NOT on the fused
+# path: the generator and the loss are plain PyTorch modules / autograd (the encoder still runs the library's
+# kernels behind autograd), trained by the reference's own loop with torch.optim.Adam.
+# --------------------------------------------------------------------------------------------------
+def vanilla_eval_minibatch(family, x, y, p_net, q_net, z_scale=1.0, ctf=None, mask=None):
+    """The reference eval_minibatch with rotate = translate = False (train_mnist.py:24-90, train_particles.py:22-148,
+    train_galaxy.py:27-128), evaluated with PyTorch ops -> (elbo, log_p_x_g_z, kl_div, y_hat)."""
+    import torch.nn.functional as F
+    b = y.size(0)
+    z_mu, z_logstd = q_net(y.reshape(b, -1))
+    z_std = torch.exp(z_logstd)
+    z = z_std * torch.empty_like(z_mu).normal_() + z_mu
+    kl_div = torch.sum(-z_logstd + 0.5 * z_std ** 2 + 0.5 * z_mu ** 2 - 0.5, 1).mean()
+    y_hat = p_net(x.expand(b, x.size(0), x.size(1)), z * z_scale)
+    if family in ("mnist", "galaxy"):
+        yv = y.reshape(b, -1)
+        log_p = -F.binary_cross_entropy(y_hat.reshape(b, -1), yv) * yv.size(1)
+    else:
+        params = y_hat.reshape(b, -1)
+        yv = y.reshape(b, -1)
+        P = yv.size(1)
+        mu, logvar = (params[:, :P], params[:, P:]) if params.size(1) > P else (params, None)
+        if ctf is not None:
+            n = int(np.sqrt(P))
+            mu = F.conv2d(mu.reshape(1, b, n, n), ctf.reshape(b, 1, ctf.size(-2), ctf.size(-1)), padding=ctf.size(-1) // 2,
+                          groups=b).reshape(b, -1)
+        if mask is not None:
+            sel = mask.reshape(-1).bool()
+            mu, yv = mu[:, sel], yv[:, sel]
+            logvar = logvar[:, sel] if logvar is not None else None
+        if logvar is not None:
+            log_p = (-0.5 * torch.sum((mu - yv) ** 2 / torch.exp(logvar) + logvar, 1)).mean()
+        else:
+            log_p = (-0.5 * torch.sum((mu - yv) ** 2, 1)).mean()
+    return log_p - kl_div, log_p, kl_div, y_hat
+
+
+def train_vanilla(family, args, x_coord, y_train, y_test, p_net, q_net, *, header, rank=0, ctf_train=None, ctf_test=None,
+                  mask=None):
+    """--vanilla training: the reference's train_epoch / eval_model loops over DataLoaders with torch.optim.Adam."""
+    print('# --vanilla: non-spatial MLP generator; plain PyTorch modules and autograd, OUTSIDE the fused B200 path',
+          file=sys.stderr)
+    optim = torch.optim.Adam(list(p_net.parameters()) + list(q_net.parameters()), lr=args.learning_rate)
+    def loader(y, c, shuffle):
+        tensors = (y,) if c is None else (y, c)
+        return torch.utils.data.DataLoader(torch.utils.data.TensorDataset(*tensors), batch_size=args.minibatch_size,
+                                           shuffle=shuffle)
+    z_scale = 1.0
+    def call(mb):
+        e, lp, kl, yh = vanilla_eval_minibatch(family, x_coord, mb[0], p_net, q_net, z_scale=z_scale,
+                                               ctf=mb[1] if len(mb) > 1 else None, mask=mask)
+        return e, lp, kl, yh
+    if rank == 0:
+        print(header)
+    for epoch in range(args.num_epochs):
+        e, err, kl = epoch_loop(loader(y_train, ctf_train, True), call, train=True, p_net=p_net, q_net=q_net, optim=optim,
+                                epoch=epoch, num_epochs=args.num_epochs, total=y_train.size(0))
+        if rank == 0:
+            print('\t'.join(map(str, [epoch, e, err, kl])), flush=True)
+        with torch.no_grad():
+            e, err, kl = epoch_loop(loader(y_test, ctf_test, False), call, train=False, p_net=p_net, q_net=q_net,
+                                    total=y_test.size(0))
+        if rank == 0:
+            print('\t'.join(map(str, [epoch, e, err, kl])), flush=True)
+    return p_net, q_net
+
+
+# --------------------------------------------------------------------------------------------------
 # epoch loops
 # --------------------------------------------------------------------------------------------------
 def make_grid(n_rows, n_cols, device=None):
@@ -182,11 +250,11 @@ def run_epoch(trainer: Trainer, x_coord, data, *, train: bool, minibatch_size: i
             y_enc = theta_offset = None
             if augment is not None:
                 y_enc, theta_offset = augment(y)
-            # single GPU: one CUDA-graph replay per minibatch (captured once per batch shape, Trainer.step_graphed);
-            # under torchrun the step is enqueued kernel by kernel (the path measured at 2/4/8 GPUs)
-            step = trainer.step_graphed if trainer.world == 1 else trainer.step
+            # one CUDA-graph replay per minibatch (captured once per batch shape, Trainer.step_graphed; the NCCL
+            # allreduce of a multi-rank step is part of the captured graph); SVAE_NO_GRAPH=1 enqueues kernel by kernel
+            step = trainer.step if os.environ.get("SVAE_NO_GRAPH") == "1" else trainer.step_graphed
             res = step(x_coord, y, global_batch=bsz, y_enc=y_enc, theta_offset=theta_offset, ctf=c, mask=mask,
-                       z_scale=z_scale)
+                       z_scale=z_scale, image_offset=lo)
         else:
             want = first_batch_hook is not None and start == 0
             res, y_hat = trainer.evaluate(x_coord, y, global_batch=bsz, ctf=c, mask=mask, want_y_hat=want,
@@ -277,9 +345,14 @@ def init_distributed(device):
 def prepare_output_dir(args, assume_yes=False):
     """outputs_<prefix>/{trained,images} wiped and recreated, command.txt written
     (reference misc_tools.py:48-74).  The reference blocks on input(); --yes or a non-tty skips it."""
-    if not assume_yes and sys.stdin.isatty():
-        if input('WARNING Will clear the outputs directory if it exists. Continue (y/n and Enter)?').lower() == 'n':
-            raise SystemExit(0)
+    out_existing = 'outputs_{}'.format(args.save_prefix)
+    if not assume_yes:
+        if sys.stdin.isatty():
+            if input('WARNING Will clear the outputs directory if it exists. Continue (y/n and Enter)?').lower() == 'n':
+                raise SystemExit(0)
+        elif os.path.isdir(out_existing):
+            # the reference always prompts; a batch job must say --yes before an existing directory is deleted
+            raise SystemExit(f"{out_existing} exists and stdin is not a terminal: pass --yes to clear it")
     import shutil
     start = datetime.datetime.now()
     print(f"Start : {start.strftime('%y%m%d_%H%M%S')}")
@@ -336,8 +409,9 @@ def export_batch_as_image(data, output, image_dims, channels_last=True):
 def add_b200_flags(parser, hyphen=False):
     """Flags this build adds on top of the reference's."""
     sep = '-' if hyphen else '_'
-    parser.add_argument('--precision', choices=['fast', 'parity'], default='fast',
-                        help='fast: bf16 tcgen05 hidden GEMMs with fp32 accumulation; parity: fp32 FFMA everywhere')
+    parser.add_argument('--precision', choices=['fast', 'parity_tc', 'parity'], default='fast',
+                        help='fast: bf16 tcgen05 hidden GEMMs with fp32 accumulation; parity_tc: 3-term bf16 splits on '
+                             'tcgen05 (fp32 accuracy); parity: fp32 FFMA everywhere')
     parser.add_argument('--seed', type=int, default=None, help='seed torch (and the shuffling) for reproducible runs')
     parser.add_argument('--yes', action='store_true', help='do not prompt before clearing the outputs directory')
     parser.add_argument(f'--synthetic', type=int, default=0,

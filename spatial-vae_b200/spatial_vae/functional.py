@@ -33,20 +33,6 @@ def set_default_precision(p: str) -> None:
     _DEFAULT_PRECISION = p
 
 
-def unvalidated_options_enabled() -> bool:
-    """--resid / --expand-coords / --bilinear are implemented in the library (option_kernels.cu, arithmetic checked
-    on the CPU against the oracle's autograd) but their GPU parity tests have not run on a B200 yet; until they
-    have, the host layer only evaluates such networks when SVAE_UNVALIDATED_OPTIONS=1."""
-    return os.environ.get("SVAE_UNVALIDATED_OPTIONS", "0") == "1"
-
-
-def require_validated(what: str) -> None:
-    if not unvalidated_options_enabled():
-        raise NotImplementedError(
-            f"{what}: implemented in libsvae_b200 but not yet validated on a B200 (tests/test_gpu_zz_options.py); "
-            "set SVAE_UNVALIDATED_OPTIONS=1 to run it anyway")
-
-
 def activation_code(act) -> int:
     """nn activation class / instance / name -> SVAE_ACT_* (LeakyReLU means slope 0.01)."""
     if isinstance(act, str):
@@ -215,8 +201,6 @@ class StepSpec:
         if dec is not None:        # the coordinate options are visible in the parameter shapes (models.py:65-75)
             c.expand_coords = int(dec.coord_w.shape[1] == 5)
             c.bilinear = int(dec.bilinear_w is not None)
-        if c.resid or c.expand_coords or c.bilinear:
-            require_validated("resid / expand_coords / bilinear networks")
         return c
 
 
@@ -241,10 +225,15 @@ def shape_of(dec: DecoderTensors, enc: Sequence[tuple], B: int, P: int, Cin: int
 
 
 def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: torch.Tensor, y: torch.Tensor,
-             eps: torch.Tensor, *, y_enc=None, theta_offset=None, ctf=None, mask=None, grad_dec=None, grad_enc=None,
-             grad_scale: Optional[float] = None, want_y_hat=False, want_latent=False):
-    """Enqueue one svae_step.  Returns (stats (B,3), y_hat or None, latent or None)."""
-    _require_cuda(grid, y, eps, dec.coord_w, enc[0][0])
+             eps: Optional[torch.Tensor], *, y_enc=None, theta_offset=None, ctf=None, mask=None, grad_dec=None,
+             grad_enc=None, grad_scale: Optional[float] = None, want_y_hat=False, want_latent=False, rng=None):
+    """Enqueue one svae_step.  Returns (stats (B,3), y_hat or None, latent or None).
+    eps None: the library draws it in the kernel from rng = (seed, step_counter (int32 device tensor), global index of
+    this call's first image): Philox keyed on (seed, step, global image index), independent of how a minibatch is split
+    across ranks."""
+    if eps is None and rng is None:
+        raise ValueError("run_step needs eps or rng=(seed, step_tensor, image_offset)")
+    _require_cuda(grid, y, dec.coord_w, enc[0][0], *([eps] if eps is not None else [rng[1]]))
     dev = y.device
     B, P = y.shape[0], grid.shape[0]
     Cin = y[0].numel() // P if B > 0 else max(1, enc[0][0].shape[1] // P)
@@ -262,6 +251,14 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
     ws = workspace(nbytes.value, dev)
 
     grid, y, eps = _f32(grid), _f32(y.reshape(B, P * Cin)), _f32(eps)
+    if y.shape[1] != enc[0][0].shape[1]:
+        raise ValueError(f"the inference network expects {enc[0][0].shape[1]} inputs per image, y has {y.shape[1]}")
+    if eps is not None and tuple(eps.shape) != (B, shape.I):
+        raise ValueError(f"eps must be ({B}, {shape.I}), got {tuple(eps.shape)}")
+    if ctf is not None and tuple(ctf.shape[-2:]) != (k_ctf, k_ctf):
+        raise ValueError("ctf kernels must be square")
+    if mask is not None and mask.numel() != P:
+        raise ValueError(f"mask must have {P} elements")
     y_enc = _f32(y_enc.reshape(B, P * Cin)) if y_enc is not None else None
     theta_offset = _f32(theta_offset)
     ctf = _f32(ctf)
@@ -270,6 +267,11 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
     inp = L.SvaeStepInputs()
     inp.grid, inp.y, inp.y_enc, inp.theta_offset = _ptr(grid), _ptr(y), _ptr(y_enc), _ptr(theta_offset)
     inp.eps, inp.ctf, inp.mask = _ptr(eps), _ptr(ctf), _ptr(mask_u8)
+    if eps is None:
+        seed, step_t, image_offset = rng
+        if step_t.dtype != torch.int32:
+            raise ValueError("rng step counter must be an int32 device tensor")
+        inp.rng_step, inp.rng_seed, inp.rng_image_offset = step_t.data_ptr(), int(seed) & (2 ** 64 - 1), int(image_offset)
     stats = torch.empty(B, 3, dtype=torch.float32, device=dev)
     y_hat = torch.empty(B, P, shape.C, dtype=torch.float32, device=dev) if want_y_hat else None
     latent = torch.empty(B, shape.I, dtype=torch.float32, device=dev) if want_latent else None
@@ -393,7 +395,6 @@ def encoder_forward(q_net, x: torch.Tensor) -> torch.Tensor:
     flat = [t for p in pairs for t in p]
     act = q_net.activation_code
     if getattr(q_net, "resid", False):
-        require_validated("resid InferenceNetwork")
         act |= L.ENC_RESID
     return _EncoderFn.apply(act, x, *flat)
 
@@ -450,8 +451,6 @@ class _DecoderFn(torch.autograd.Function):
 
 def decoder_forward(p_net, x: torch.Tensor, z: Optional[torch.Tensor]) -> torch.Tensor:
     dec = decoder_tensors_of(p_net)
-    if getattr(p_net, "resid", False) or dec.bilinear_w is not None or dec.coord_w.shape[1] == 5:
-        require_validated("resid / expand_coords / bilinear SpatialGenerator")
     meta = (p_net.activation_code, bool(p_net.softplus), getattr(p_net, "precision", None) or default_precision(),
             bool(getattr(p_net, "resid", False)), dec.layout())
     return _DecoderFn.apply(meta, x, z, *dec.flat())
@@ -585,3 +584,36 @@ def gemm_dw_top(h_top: torch.Tensor, h_prev: torch.Tensor, g_o: torch.Tensor, ou
                                    out_w.data_ptr(), d_out_w.data_ptr(), d_out_b.data_ptr(), d_b.data_ptr(),
                                    dW.data_ptr(), _ptr(delta), _stream()), "svae_gemm_dw_top")
     return dW, d_out_w, d_out_b, d_b, delta
+
+
+class _ResidLinearFn(torch.autograd.Function):
+    """act(x W^T + b + x) (reference models.py:20-21) on the library's fp32 GEMM with the skip connection in its epilogue."""
+
+    @staticmethod
+    def forward(ctx, act, x, w, b):
+        _require_cuda(x, w, b)
+        xf = _f32(x.reshape(-1, x.shape[-1]))
+        wf, bf = _f32(w.detach()), _f32(b.detach())
+        out = torch.empty_like(xf)
+        L.check(L.lib.svae_resid_linear_forward(xf.data_ptr(), wf.data_ptr(), bf.data_ptr(), out.data_ptr(), xf.shape[0],
+                                                xf.shape[1], act, _stream()), "svae_resid_linear_forward")
+        ctx.act = act
+        ctx.save_for_backward(xf, wf, out)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        xf, wf, out = ctx.saved_tensors
+        gf = _f32(g.reshape(out.shape))
+        g_pre, g_x = torch.empty_like(out), torch.empty_like(out)
+        g_w, g_b = torch.zeros_like(wf), torch.zeros(wf.shape[0], dtype=torch.float32, device=wf.device)
+        L.check(L.lib.svae_resid_linear_backward(xf.data_ptr(), wf.data_ptr(), out.data_ptr(), gf.data_ptr(),
+                                                 g_pre.data_ptr(), g_x.data_ptr(), g_w.data_ptr(), g_b.data_ptr(),
+                                                 xf.shape[0], xf.shape[1], ctx.act, _stream()), "svae_resid_linear_backward")
+        return None, g_x.view(g.shape), g_w, g_b
+
+
+def resid_linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, act: int) -> torch.Tensor:
+    if w.shape[0] != w.shape[1] or x.shape[-1] != w.shape[1]:
+        raise ValueError("ResidLinear needs a square weight matching the input width (x + linear(x))")
+    return _ResidLinearFn.apply(act, x, w, b)

@@ -4,9 +4,8 @@ Same classes, constructor arguments, attribute names and state_dict keys as the 
 module (reference spatial_vae/models.py:13-172), so whole-module `.sav` pickles and state
 dicts interchange.  The submodules only HOLD the parameters; `forward` hands them to the
 sm_100a kernels in libsvae_b200.so through `spatial_vae.functional` (no eager arithmetic, no CPU
-fallback).  The options resid / expand_coords / bilinear run through option_kernels.cu; until their GPU
-parity tests have run on a B200 they are gated behind SVAE_UNVALIDATED_OPTIONS=1
-(spatial_vae.functional.require_validated).
+fallback).  The options resid / expand_coords / bilinear run through option_kernels.cu (GPU parity tests:
+tests/test_gpu_zz_options.py).
 """
 from __future__ import annotations
 
@@ -32,9 +31,9 @@ def _stack(first_in, width, depth, act, resid):
 
 
 class ResidLinear(nn.Module):
-    """act(linear(x) + x) (reference models.py:13-21).  Parameter container: the networks that own it evaluate
-    it inside their own fused forward (the skip connection rides in the GEMM epilogue, or in W + I on the
-    tensor-core path); it has no kernel of its own."""
+    """act(linear(x) + x) (reference models.py:13-21).  Inside InferenceNetwork / SpatialGenerator it is evaluated as
+    part of the network's fused forward (the skip connection rides in the GEMM epilogue); called on its own it runs
+    the same fp32 GEMM-with-addend through svae_resid_linear_forward / _backward (autograd supported)."""
 
     def __init__(self, n_in, n_out, activation=nn.Tanh):
         super().__init__()
@@ -42,7 +41,7 @@ class ResidLinear(nn.Module):
         self.act = activation()
 
     def forward(self, x):
-        raise NotImplementedError("ResidLinear is evaluated as part of InferenceNetwork / SpatialGenerator")
+        return SF.resid_linear(x, self.linear.weight, self.linear.bias, SF.activation_code(type(self.act)))
 
 
 class _Derived:

@@ -42,7 +42,10 @@ class FlatParams:
             off += (n + 3) // 4 * 4
         self.total = off
         self.data = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros_like(self.data)
+        # the gradient buffer carries 4 extra floats: the per-rank loss sums (logp, kl, elbo, unused) ride in the
+        # same allreduce as the gradient
+        self.grad_ext = torch.zeros(off + 4, dtype=torch.float32, device=dev)
+        self.grad = self.grad_ext[:off]
         self.m = torch.zeros_like(self.data)
         self.v = torch.zeros_like(self.data)
         for p, o, n in zip(params, self.offsets, self.numels):
@@ -59,7 +62,7 @@ class Trainer:
     slice of the global minibatch and leaves (elbo, logp, kl) batch means on the device."""
 
     def __init__(self, p_net, q_net, spec: SF.StepSpec, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None):
+                 process_group=None, seed: Optional[int] = None):
         if bool(getattr(p_net, "resid", False)) != bool(getattr(q_net, "resid", False)):
             raise NotImplementedError("one resid flag for both networks, as the reference's --resid")
         if bool(getattr(p_net, "resid", False)) != bool(spec.resid):
@@ -75,6 +78,21 @@ class Trainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        if self.world > 1:
+            # data-parallel replicas start from rank 0's weights whatever each process initialised (the reference
+            # never seeds, train_mnist.py has no manual_seed); Adam moments and the step counter start at zero
+            dist.broadcast(self.flat.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                           group=process_group)
+        # eps: drawn in the kernel (Philox keyed on seed, step, GLOBAL image index), so an N-rank run draws the
+        # same numbers as a single-rank run of the same minibatch.  The seed is shared by all ranks.
+        if seed is None:
+            seed_t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+            if self.world > 1:
+                seed_t = seed_t.to(dev)
+                dist.broadcast(seed_t, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
+            seed = int(seed_t.item())
+        self.seed = seed
         self._bind()
 
     def _bind(self):
@@ -89,35 +107,20 @@ class Trainer:
     # -- one train step ---------------------------------------------------------------------------
     def step(self, x_coord: torch.Tensor, y_local: torch.Tensor, *, global_batch: Optional[int] = None,
              eps: Optional[torch.Tensor] = None, y_enc=None, theta_offset=None, ctf=None, mask=None,
-             z_scale: Optional[float] = None) -> torch.Tensor:
+             z_scale: Optional[float] = None, image_offset: Optional[int] = None) -> torch.Tensor:
         """y_local: this rank's images.  global_batch: images over all ranks (default: local size x world
-        when every rank holds the same count).  Returns a device tensor [elbo, logp, kl] (global batch
-        means); nothing is synchronised with the host."""
-        B_local = y_local.shape[0]
-        B_global = global_batch if global_batch is not None else B_local * self.world
-        spec = self.spec
-        if z_scale is not None and z_scale != spec.z_scale:
-            spec = SF.StepSpec(**{**spec.__dict__, "z_scale": z_scale})
-        I = self.enc[-1][0].shape[0] // 2
-        if eps is None:
-            eps = torch.empty(B_local, I, dtype=torch.float32, device=y_local.device).normal_()
-        stats, _, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc,
-                                  theta_offset=theta_offset, ctf=ctf, mask=mask, grad_dec=self.gdec,
-                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1))
-        sums = stats.sum(0) if B_local > 0 else stats.new_zeros(3)
-        if self.world > 1:
-            # the one exchange step of the path: gradient sum (+ the three loss sums) across ranks
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+        when every rank holds the same count).  eps None: drawn in the kernel (see __init__); image_offset is the
+        global minibatch index of y_local[0] (default: rank * local size).  Returns a device tensor [elbo, logp, kl]
+        (global batch means); nothing is synchronised with the host."""
+        B_global = global_batch if global_batch is not None else y_local.shape[0] * self.world
+        out = self._step_body(x_coord, y_local, B_global, eps, y_enc, theta_offset, ctf, mask, z_scale, image_offset)
         self.t += 1
-        SF.adam_step_graph(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t_dev, self.bc_dev,
-                           self.betas, self.adam_eps, zero_grad=True)
-        means = sums / max(B_global, 1)
-        return torch.stack([means[2], means[0], means[1]])
+        return out
 
     # -- the same step replayed from a CUDA graph ------------------------------------------------------
     def step_graphed(self, x_coord: torch.Tensor, y_local: torch.Tensor, *, global_batch: Optional[int] = None,
-                     ctf=None, mask=None, y_enc=None, theta_offset=None, z_scale: Optional[float] = None) -> torch.Tensor:
+                     ctf=None, mask=None, y_enc=None, theta_offset=None, z_scale: Optional[float] = None,
+                     image_offset: Optional[int] = None) -> torch.Tensor:
         """`step` with the ~40 kernel launches (+ the NCCL allreduce) of one train step captured once per input
         shape into a CUDA graph and replayed: the inputs are copied into static buffers, eps is drawn inside the
         graph, Adam's step counter and bias corrections live in device memory.  The first call for a
@@ -126,12 +129,12 @@ class Trainer:
         B_local = y_local.shape[0]
         B_global = global_batch if global_batch is not None else B_local * self.world
         key = (tuple(y_local.shape), B_global, None if ctf is None else tuple(ctf.shape), mask is not None,
-               y_enc is not None, theta_offset is not None, z_scale)
+               y_enc is not None, theta_offset is not None, z_scale, image_offset)
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs[key] = "warm"
             return self.step(x_coord, y_local, global_batch=global_batch, ctf=ctf, mask=mask, y_enc=y_enc,
-                             theta_offset=theta_offset, z_scale=z_scale)
+                             theta_offset=theta_offset, z_scale=z_scale, image_offset=image_offset)
         if entry == "warm":
             st = {"y": y_local.clone(), "ctf": ctf.clone() if ctf is not None else None,
                   "y_enc": y_enc.clone() if y_enc is not None else None,
@@ -140,7 +143,7 @@ class Trainer:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 st["out"] = self._step_body(x_coord, st["y"], B_global, None, st["y_enc"], st["toff"], st["ctf"], mask,
-                                            z_scale)
+                                            z_scale, image_offset)
             st["graph"] = graph
             # the captured kernels hold raw pointers into the library workspace: keep that buffer alive even if a
             # later, larger request makes spatial_vae.functional.workspace() allocate a new one
@@ -159,26 +162,32 @@ class Trainer:
         st["graph"].replay()
         return st["out"]
 
-    def _step_body(self, x_coord, y_local, B_global, eps, y_enc, theta_offset, ctf, mask, z_scale):
+    def _step_body(self, x_coord, y_local, B_global, eps, y_enc, theta_offset, ctf, mask, z_scale, image_offset=None):
         """Everything of one train step that is enqueued on the stream (shared by step_graphed's capture)."""
         B_local = y_local.shape[0]
         spec = self.spec
         if z_scale is not None and z_scale != spec.z_scale:
             spec = SF.StepSpec(**{**spec.__dict__, "z_scale": z_scale})
-        I = self.enc[-1][0].shape[0] // 2
+        rng = None
         if eps is None:
-            eps = torch.empty(B_local, I, dtype=torch.float32, device=y_local.device).normal_()
+            off = image_offset if image_offset is not None else self.rank * B_local
+            rng = (self.seed, self.t_dev, off)          # t_dev: Adam's device-resident step counter (steps done so far)
         stats, _, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc,
                                   theta_offset=theta_offset, ctf=ctf, mask=mask, grad_dec=self.gdec,
-                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1))
-        sums = stats.sum(0) if B_local > 0 else stats.new_zeros(3)
+                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1), rng=rng)
+        tail = self.flat.grad_ext[self.flat.total:]
+        if B_local > 0:
+            tail[:3].copy_(stats.sum(0))
+        else:
+            tail.zero_()
         if self.world > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+            # the one exchange step of the path: gradient sum and the three loss sums in ONE allreduce
+            dist.all_reduce(self.flat.grad_ext, op=dist.ReduceOp.SUM, group=self.pg)
+        means = tail[:3] / max(B_global, 1)
+        out = torch.stack([means[2], means[0], means[1]])
         SF.adam_step_graph(self.flat.data, self.flat.grad, self.flat.m, self.flat.v, self.lr, self.t_dev, self.bc_dev,
                            self.betas, self.adam_eps, zero_grad=True)
-        means = sums / max(B_global, 1)
-        return torch.stack([means[2], means[0], means[1]])
+        return out
 
     @torch.no_grad()
     def evaluate(self, x_coord, y_local, *, global_batch=None, eps=None, ctf=None, mask=None, want_y_hat=False,

@@ -100,8 +100,6 @@ def galaxy_arguments(argv=None):
 
 def main(argv=None):
     args = galaxy_arguments(argv)
-    if args.vanilla:
-        raise SystemExit('--vanilla is outside the B200 fused path; run it with the reference implementation')
     device = D.pick_device(args.device)
     rank = D.init_distributed(device)
     if args.seed is not None:
@@ -143,6 +141,15 @@ def main(argv=None):
 
     print('# training with z-dim:', args.z_dim, file=sys.stderr)
     activation = D.activation_from_flag(args.activation, 'galaxy')
+    if args.vanilla:      # reference train_galaxy.py: standard MLP generator, no rotation / translation inference
+        print('# using the vanilla MLP generator architecture', file=sys.stderr)
+        p_net = models.VanillaGenerator(rows * cols, args.z_dim, args.p_hidden_dim, n_out=channels,
+                                        num_layers=args.p_num_layers, activation=activation).to(device)
+        q_net = models.InferenceNetwork(channels * rows * cols, args.z_dim, args.q_hidden_dim,
+                                        num_layers=args.q_num_layers, activation=activation).to(device)
+        D.train_vanilla('galaxy', args, x_coord, y_train, y_val, p_net, q_net,
+                        header='\t'.join(['Epoch', 'ELBO', 'BCE loss', 'KL']), rank=rank)
+        return
     print('# using the spatial generator architecture', file=sys.stderr)
     rotate, translate = not args.no_rotate, not args.no_translate
     inf_dim = args.z_dim + (1 if rotate else 0) + (2 if translate else 0)

@@ -111,9 +111,6 @@ def load_images(args):
 
 def main(argv=None):
     args = mnist_arguments(argv)
-    if args.vanilla:
-        raise SystemExit('--vanilla uses the non-spatial MLP generator, which is outside the B200 fused path; '
-                         'run it with the reference implementation')
     device = D.pick_device(args.device)
     rank = D.init_distributed(device)
     if args.seed is not None:
@@ -135,6 +132,17 @@ def main(argv=None):
     z_dim = args.z_dim
     print('# training with z-dim:', z_dim, file=sys.stderr)
     activation = D.activation_from_flag(args.activation, 'mnist')
+    if args.vanilla:      # reference train_mnist.py:351-357: standard MLP generator, no rotation / translation inference
+        print('# using the vanilla MLP generator architecture', file=sys.stderr)
+        p_net = models.VanillaGenerator(n * m, z_dim, args.p_hidden_dim, num_layers=args.num_layers,
+                                        activation=activation).to(device)
+        q_net = models.InferenceNetwork(n * m, z_dim, args.q_hidden_dim, num_layers=args.num_layers,
+                                        activation=activation).to(device)
+        D.train_vanilla('mnist', args, x_coord, y_train, y_test, p_net, q_net,
+                        header='\t'.join(['Epoch', 'ELBO', 'BCE loss', 'KL']), rank=rank)
+        if rank == 0:
+            D.save_models(args.save_prefix, str(args.num_epochs).zfill(digits), trained_dir, p_net, q_net, device)
+        return
     print('# using the spatial generator architecture', file=sys.stderr)
     rotate, translate = not args.no_rotate, not args.no_translate
     inf_dim = z_dim + (1 if rotate else 0) + (2 if translate else 0)

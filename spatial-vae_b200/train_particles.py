@@ -98,12 +98,6 @@ load_images = D.load_particle_stack
 
 def main(argv=None):
     args = parse(argv)
-    if args.vanilla:
-        raise SystemExit('--vanilla uses the non-spatial MLP generator, which is outside the B200 fused path; '
-                         'run it with the reference implementation')
-    if (args.resid or args.expand_coords or args.bilinear) and not SF.unvalidated_options_enabled():
-        raise SystemExit('--resid/--expand-coords/--bilinear are implemented in libsvae_b200 but their GPU parity '
-                         'tests have not run on a B200 yet; set SVAE_UNVALIDATED_OPTIONS=1 to train with them')
     if args.fit_noise and args.ctf_train is not None:
         raise SystemExit('--fit-noise cannot be combined with CTF filtering (the reference crashes on it, '
                          'train_particles.py:121-124,137)')
@@ -153,6 +147,17 @@ def main(argv=None):
 
     print('# training with z-dim:', args.z_dim, file=sys.stderr)
     activation = D.activation_from_flag(args.activation, 'particles')
+    if args.vanilla:      # reference train_particles.py:425-431: standard MLP generator, no rotation / translation inference
+        print('# using the vanilla MLP generator architecture', file=sys.stderr)
+        p_net = models.VanillaGenerator(n * m, args.z_dim, args.p_hidden_dim, n_out=2 if args.fit_noise else 1,
+                                        num_layers=args.p_num_layers, activation=activation,
+                                        softplus=args.softplus).to(device)
+        q_net = models.InferenceNetwork(n * m, args.z_dim, args.q_hidden_dim, num_layers=args.q_num_layers,
+                                        activation=activation).to(device)
+        D.train_vanilla('particles', args, x_coord, y_train, y_test, p_net, q_net,
+                        header='\t'.join(['Epoch', 'Split', 'ELBO', 'Error', 'KL']), rank=rank, ctf_train=ctf_train,
+                        ctf_test=ctf_test, mask=mask)
+        return
     print('# using the spatial generator architecture', file=sys.stderr)
     rotate, translate = not args.no_rotate, not args.no_translate
     inf_dim = args.z_dim + (1 if rotate else 0) + (2 if translate else 0)

@@ -41,7 +41,6 @@ def install(monkeypatch, fresh_copy_dir=None):
         return ws
 
     monkeypatch.setattr(SF, "workspace", workspace)
-    monkeypatch.setenv("SVAE_UNVALIDATED_OPTIONS", "1")
     return emu
 
 

@@ -51,6 +51,8 @@ inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x,
 inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 
 // ---- bf16 (round to nearest even, like the _rn intrinsics) --------------------------------------------------
 struct __nv_bfloat16 { uint16_t bits; };

@@ -115,9 +115,10 @@ def test_same_seed_gives_reference_parameter_init(built):
         np.testing.assert_array_equal(v.numpy(), d["q." + k])
 
 
-def test_unvalidated_options_are_gated(built, monkeypatch):
-    """resid / expand_coords / bilinear run through option_kernels.cu, but only behind SVAE_UNVALIDATED_OPTIONS=1
-    until tests/test_gpu_zz_options.py has passed on a B200; either way there is no CPU path."""
+def test_option_networks_have_no_cpu_path_either(built):
+    """resid / expand_coords / bilinear run through option_kernels.cu by default (their GPU parity tests are green:
+    tests/test_gpu_zz_options.py); like everything else they refuse CPU tensors instead of falling back, and a
+    standalone ResidLinear goes through the library as well."""
     import spatial_vae.models as M
     with contextlib.redirect_stdout(io.StringIO()):
         nets = [M.SpatialGenerator(3, 16, resid=True, num_layers=2), M.SpatialGenerator(3, 16, expand_coords=True),
@@ -126,18 +127,13 @@ def test_unvalidated_options_are_gated(built, monkeypatch):
     assert [k for k, _ in nets[2].named_parameters()][:4] == ["coord_linear.weight", "coord_linear.bias",
                                                               "latent_linear.weight", "bilinear.weight"]
     assert "layers.1.linear.weight" in dict(nets[0].named_parameters())
-    monkeypatch.delenv("SVAE_UNVALIDATED_OPTIONS", raising=False)
-    for p in nets:
-        with pytest.raises(NotImplementedError, match="SVAE_UNVALIDATED_OPTIONS"):
-            p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
-    with pytest.raises(NotImplementedError, match="SVAE_UNVALIDATED_OPTIONS"):
-        q(torch.zeros(2, 8))
-    monkeypatch.setenv("SVAE_UNVALIDATED_OPTIONS", "1")
     for p in nets:
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             p(torch.zeros(1, 4, 2), torch.zeros(1, 3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         q(torch.zeros(2, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.ResidLinear(8, 8)(torch.zeros(2, 8))
 
 
 def test_decoder_tensor_layout_follows_parameter_order(built):

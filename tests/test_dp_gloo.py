@@ -30,10 +30,15 @@ def _free_port():
 
 def _install_doubles(SF):
     def fake_run_step(spec, dec, enc, grid, y, eps, *, y_enc=None, theta_offset=None, ctf=None, mask=None,
-                      grad_dec=None, grad_enc=None, grad_scale=None, want_y_hat=False, want_latent=False):
+                      grad_dec=None, grad_enc=None, grad_scale=None, want_y_hat=False, want_latent=False, rng=None):
         B = y.shape[0]
         if B == 0:
             return torch.zeros(0, 3), None, None
+        if eps is None:      # stand-in for the in-kernel draw: a function of (seed, step, GLOBAL image index) only
+            seed, step_t, off = rng
+            I = enc[-1][0].shape[0] // 2
+            eps = torch.stack([torch.randn(I, generator=torch.Generator().manual_seed(
+                (seed + 1000003 * int(step_t) + 7919 * (off + b)) % (2 ** 31))) for b in range(B)])
         cfg = O.StepConfig(family=spec.family, rotate=spec.rotate, translate=spec.translate, dx_scale=spec.dx_scale,
                            theta_prior=spec.theta_prior, z_scale=spec.z_scale, softplus=spec.softplus,
                            resid=spec.resid)
@@ -254,3 +259,68 @@ def test_two_rank_run_epoch_on_the_simt_emulation(tmp_path, family):
     counts = torch.bincount(seen, minlength=21)
     assert torch.equal(counts, torch.full((21,), 2)), counts   # once in the training pass, once in validation
     assert torch.isfinite(r0["stats"]).all()
+
+
+def _bcast_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import spatial_vae.functional as SF
+        import spatial_vae.models as M
+        from spatial_vae.trainer import Trainer, shard_bounds
+        from tests import emu_backend
+        emu_backend.install(pytest.MonkeyPatch())
+        torch.manual_seed(50 + rank)                     # every rank initialises DIFFERENT weights (no --seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2)
+            q = M.InferenceNetwork(36, 6, 12, num_layers=2)
+        before = torch.cat([t.detach().reshape(-1).clone() for t in list(p.parameters()) + list(q.parameters())])
+        tr = Trainer(p, q, SF.StepSpec(family="mnist", theta_prior=0.7, precision="parity"), lr=1e-3)
+        flat = tr.flat.data.clone()
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert all(torch.equal(gathered[0], g) for g in gathered), "replicas differ after construction"
+        seeds = [None] * world
+        dist.all_gather_object(seeds, tr.seed)
+        assert len(set(seeds)) == 1, "ranks must share the eps seed"
+        # in-kernel eps: two steps on a ragged split; the result must not depend on the split
+        g = torch.Generator().manual_seed(9)
+        grid = O.make_grid(6, 6)
+        out = []
+        for B in (5, 4):
+            y = (torch.rand(B, 36, generator=g) > 0.7).float() * torch.rand(B, 36, generator=g)
+            lo, hi = shard_bounds(B, world, rank)
+            out.append(tr.step(grid, y[lo:hi], global_batch=B, image_offset=lo).clone())
+        if rank == 0:
+            torch.save({"before_rank0": before, "flat": tr.flat.data.clone(), "seed": tr.seed, "out": torch.stack(out)}, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_start_equal_and_in_kernel_eps_is_split_invariant(tmp_path, monkeypatch):
+    """Trainer broadcasts rank 0's initial weights (the CLIs do not seed by default) and shares the eps seed; with eps
+    drawn in the kernel (Philox keyed on seed, step, global image index) a 2-rank run on a ragged split reproduces the
+    single-process trajectory from the same weights.  Runs the real C ABI on tests/simt_emu."""
+    from tests.simt_emu.build import build
+    build()
+    tmp = str(tmp_path / "bc.pt")
+    mp.spawn(_bcast_worker, args=(2, _free_port(), tmp), nprocs=2, join=True)
+    got = torch.load(tmp)
+    import spatial_vae.functional as SF
+    import spatial_vae.models as M
+    from spatial_vae.trainer import Trainer
+    from tests import emu_backend
+    emu_backend.install(monkeypatch)
+    torch.manual_seed(50)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p = M.SpatialGenerator(3, 16, n_out=1, num_layers=2)
+        q = M.InferenceNetwork(36, 6, 12, num_layers=2)
+    tr = Trainer(p, q, SF.StepSpec(family="mnist", theta_prior=0.7, precision="parity"), lr=1e-3, seed=got["seed"])
+    g = torch.Generator().manual_seed(9)
+    grid = O.make_grid(6, 6)
+    out = []
+    for B in (5, 4):
+        y = (torch.rand(B, 36, generator=g) > 0.7).float() * torch.rand(B, 36, generator=g)
+        out.append(tr.step(grid, y).clone())
+    np.testing.assert_allclose(got["out"].numpy(), torch.stack(out).numpy(), rtol=2e-5)
+    np.testing.assert_allclose(got["flat"].numpy(), tr.flat.data.numpy(), rtol=1e-4, atol=1e-6)

@@ -5,8 +5,8 @@ the late tests that only use kernels already validated on hardware).
 fixtures tests/golden/particles_opt_*.npz and the oracle (reference models.py:13-21,65-67,74-75,99-102,114-121), the
 particle driver without theta / dx, whole-module pickles written by the reference.  (2) svae_ctf_filter.  (3) The
 seeded random configurations of tests/test_emu_fuzz.py on the device.  (4) ResidLinear on the tcgen05 route
-(SVAE_RESID_TC=1).  Every body has passed on the emulation (tests/test_emu_gpu_suite.py).  The host-side gate
-SVAE_UNVALIDATED_OPTIONS stays in the product until this file has been seen green on a GPU.
+(SVAE_RESID_TC=1).  Every body has passed on the emulation (tests/test_emu_gpu_suite.py) and on a B200 (round 1's driver run), after which
+the host-side gate SVAE_UNVALIDATED_OPTIONS was removed.
 """
 import contextlib
 import io
@@ -26,11 +26,6 @@ from tests.test_gpu_api import _inject_normal, _nets, _script
 
 OPTION_CASES = ["particles_opt_resid", "particles_opt_expand", "particles_opt_bilinear", "particles_opt_softplus",
                 "particles_opt_all", "particles_t_only", "particles_r_only"]   # + the particle driver without theta / dx
-
-
-@pytest.fixture(autouse=True)
-def _lift_gate(monkeypatch):
-    monkeypatch.setenv("SVAE_UNVALIDATED_OPTIONS", "1")
 
 
 def _cuda():
