@@ -8,6 +8,7 @@ tcgen05 hidden GEMMs, fp32 accumulate) is held to the north-star ELBO tolerance.
 import contextlib
 import io
 import math
+import os
 
 import numpy as np
 import pytest
@@ -410,12 +411,15 @@ def test_inference_network_module_forward_backward():
 
 
 # ---- 10-step Adam trajectory -------------------------------------------------------------------------
-@pytest.mark.parametrize("precision", ["parity", "fast"])
+@pytest.mark.parametrize("precision", ["parity", "parity_tc", "fast"])
 def test_adam_trajectory_matches_reference(precision):
-    """Reference loop (eval_minibatch, backward, Adam.step, zero_grad) x10 on the golden fixture:
-    parameters within 1e-4 (north star).  FAST precision is reported: Adam turns tiny relative
-    gradient noise on near-zero gradients into O(lr) differences, so the bound for it
-    is the fraction of parameters within tolerance."""
+    """Reference loop (eval_minibatch, backward, Adam.step, zero_grad) x10 on the golden fixture (written by the
+    reference itself): parameters within 1e-4 (north star) for PARITY (fp32 FFMA) AND for PARITY_TC (3-term bf16
+    splits on tcgen05).  FAST (single bf16 pass) cannot meet the max-abs gate -- Adam turns relative gradient noise
+    on near-zero gradients into O(lr) differences -- so it is held to what bounds a trajectory: the
+    fraction of parameters within 1e-4, the mean absolute difference, and the relative L2 error of the total
+    10-step update (test_adam_trajectory_at_c1_shape); on THIS fixture all three modes are inside 1e-4.  The
+    measured values are written to gpurun_out/parity_trajectory_<precision>.json."""
     dev = _cuda()
     SF = _sf()
     d = load_case("mnist_adam10")
@@ -451,13 +455,93 @@ def test_adam_trajectory_matches_reference(precision):
     fdec, fenc = oracle_params(d, p_prefix="final.p.", q_prefix="final.q.")
     ref = torch.cat([p.reshape(-1) for p in O.flatten_params(fdec, fenc)])
     diff = (flat.cpu() - ref).abs()
-    np.testing.assert_allclose(elbos, d["elbos"], rtol=1e-4 if precision == "parity" else 1e-3)
-    if precision == "parity":
-        assert float(diff.max()) < 1e-4, float(diff.max())
+    np.testing.assert_allclose(elbos, d["elbos"], rtol=1e-4 if precision != "fast" else 1e-3)
+    idec, ienc = oracle_params(d, p_prefix="init.p.", q_prefix="init.q.")
+    init = torch.cat([p.reshape(-1) for p in O.flatten_params(idec, ienc)])
+    frac = float((diff < 1e-4).float().mean())
+    rel_update = float((flat.cpu() - ref).norm() / (ref - init).norm())
+    rec = {"precision": precision, "max_abs_dparam": float(diff.max()), "mean_abs_dparam": float(diff.mean()),
+           "frac_within_1e-4": frac, "rel_l2_error_of_10_step_update": rel_update,
+           "max_rel_elbo_err": float(np.max(np.abs(np.array(elbos) - d["elbos"]) / np.abs(d["elbos"])))}
+    print(rec)
+    try:
+        import json
+        os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                               f"parity_trajectory_{precision}.json"), "w") as f:
+            json.dump(rec, f)
+    except OSError:
+        pass
+    # every precision meets the north-star gate on this fixture (measured on a B200: max |dparam| 1.5e-8 PARITY,
+    # 3.0e-8 PARITY_TC, 6.2e-6 FAST); the C1-shape trajectory below is the harder case for FAST
+    assert float(diff.max()) < 1e-4, rec
+    if precision == "fast":
+        assert rel_update < 0.01, rec
+
+
+@pytest.mark.parametrize("precision", ["parity_tc", "fast"])
+def test_adam_trajectory_at_c1_shape(precision):
+    """10 Adam steps at the C1 MODEL shape (28x28, z = 2, 500x2, q 500x2; 32 images per step) against the oracle's
+    trajectory from the same initial parameters and eps: PARITY_TC is inside the north-star 1e-4 on every parameter;
+    FAST (one bf16 pass) is not expected to be (SURVEY 7.2 measured 3.6e-4 for it in emulation: Adam's m / sqrt(v)
+    turns relative gradient noise on near-zero gradients into O(lr) steps), so it is bounded by what a 10-step
+    trajectory at lr = 1e-4 allows -- > 99.9 % of parameters inside 1e-4, the largest deviation below 10 lr, the
+    total update within 2 % of the reference's in L2 -- and its measured values are recorded."""
+    import bench
+    import json
+    dev = _cuda()
+    SF = _sf()
+    c = dict(bench.CONFIGS["c1"])
+    P, B, steps, lr = c["n"] * c["n"], 32, 10, 1e-4
+    dec, enc = O.init_params(P, c["Z"] + 3, c["Z"], c["H"], c["L"], c["Hq"], c["Lq"], c["C"], seed=2)
+    cfg = O.StepConfig(family="mnist", theta_prior=c["theta_prior"])
+    grid = O.make_grid(c["n"], c["n"])
+    ys = [bench.synth_images(c, B, torch.device("cpu"), 500 + t) for t in range(steps)]
+    epss = [torch.randn(B, c["Z"] + 3, generator=torch.Generator().manual_seed(1000 + t)) for t in range(steps)]
+    init = torch.cat([p.reshape(-1) for p in O.flatten_params(dec, enc)]).clone()
+    dec_o, enc_o, elbos_ref = O.train_steps(cfg, dec, enc, grid, ys, epss, lr=lr)
+    ref = torch.cat([p.reshape(-1) for p in O.flatten_params(dec_o, enc_o)])
+    dd, ee = _to_dev(dec, enc, dev)
+    params = dd.flat() + [t for pair in ee for t in pair]
+    flat = torch.cat([p.reshape(-1) for p in params]).clone()
+    gflat, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    def views(buf):
+        out, off = [], 0
+        for p in params:
+            out.append(buf[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return out
+    n_dec = len(dd.flat())
+    pv, gv = views(flat), views(gflat)
+    dd = SF.DecoderTensors.from_flat(pv[:n_dec], dd.latent_w is not None, len(dd.hidden))
+    ee = [(pv[n_dec + i], pv[n_dec + i + 1]) for i in range(0, len(pv) - n_dec, 2)]
+    gd = SF.DecoderTensors.from_flat(gv[:n_dec], dd.latent_w is not None, len(dd.hidden))
+    ge = [(gv[n_dec + i], gv[n_dec + i + 1]) for i in range(0, len(gv) - n_dec, 2)]
+    elbos = []
+    for t in range(steps):
+        stats, _, _ = SF.run_step(_spec(cfg, precision), dd, ee, grid.to(dev), ys[t].to(dev), epss[t].to(dev),
+                                  grad_dec=gd, grad_enc=ge)
+        SF.adam_step(flat, gflat, m, v, lr, t + 1)
+        elbos.append(float(stats[:, 2].mean()))
+    diff = (flat.cpu() - ref).abs()
+    rec = {"shape": "c1", "precision": precision, "max_abs_dparam": float(diff.max()), "mean_abs_dparam": float(diff.mean()),
+           "frac_within_1e-4": float((diff < 1e-4).float().mean()),
+           "rel_l2_error_of_10_step_update": float((flat.cpu() - ref).norm() / (ref - init).norm()),
+           "max_rel_elbo_err": float(np.max(np.abs(np.array(elbos) - np.array(elbos_ref)) / np.abs(np.array(elbos_ref))))}
+    print(rec)
+    try:
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, f"parity_trajectory_c1_{precision}.json"), "w") as f:
+            json.dump(rec, f)
+    except OSError:
+        pass
+    assert rec["max_rel_elbo_err"] < (1e-3 if precision == "fast" else 2e-5), rec
+    if precision == "parity_tc":
+        assert rec["max_abs_dparam"] < 1e-4, rec
     else:
-        frac = float((diff < 1e-4).float().mean())
-        print(f"fast precision: max |dparam| {float(diff.max()):.3e}, within 1e-4: {frac:.5f}")
-        assert frac > 0.99 and float(diff.max()) < 2.5e-3   # 2.5e-3 > 10 steps * lr: sign flips only
+        assert rec["frac_within_1e-4"] > 0.999 and rec["max_abs_dparam"] < 1e-3 and \
+            rec["rel_l2_error_of_10_step_update"] < 0.02, rec
 
 
 # ---- full BASELINE sizes: size-independent properties + fast-vs-parity agreement -------------------------

@@ -305,7 +305,7 @@ def _run_fuzz_step(seed):
         stats, _, _ = SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge, **kw_lib)
         torch.cuda.synchronize()
         got = stats[:, 2].cpu().numpy()
-        tol = 3e-5 if precision == "parity" else 1e-2
+        tol = 3e-5 if precision == "parity" else 1e-3          # the north star's per-image ELBO tolerance
         assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)).max() <= tol, (c, precision, got, ref)
         if precision == "parity":
             grads = [g.cpu() for g in gd.flat()] + [t.cpu() for pr in ge for t in pr]
