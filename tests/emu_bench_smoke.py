@@ -30,7 +30,7 @@ real_gen = torch.Generator
 torch.Generator = lambda device=None: real_gen()
 real_randperm = torch.randperm
 import bench
-sys.argv = ["bench.py", "--config", os.environ.get("BENCH_SMOKE_CONFIG", "c1"), "--batch", "1", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"]
+sys.argv = ["bench.py", "--config", os.environ.get("BENCH_SMOKE_CONFIG", "c1"), "--batch", "1", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras"]
 buf = io.StringIO()
 with contextlib.redirect_stdout(buf):
     bench.main()
