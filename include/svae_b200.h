@@ -14,14 +14,29 @@
  *   svae_gather_rows                   DataLoader(TensorDataset, shuffle)   train_mnist.py:334,395-396
  *   svae_rotate_bicubic                PIL Image.rotate(BICUBIC) loop       train_particles.py:28-43, train_galaxy.py:36-54
  *   svae_ctf_filter                    ctf_filter's per-particle ifft2 loop spatial_vae/ctf.py:33-56
+ *   svae_resid_linear_forward/_backward ResidLinear.forward                 spatial_vae/models.py:13-21
  *   svae_gemm_bf16                     one nn.Linear of SpatialGenerator.layers (models.py:82,126) on
  *                                      tcgen05 tensor cores (building block, exposed for tests)
+ *   svae_gemm_dw_top, svae_gemm_dx_moments  fused head / tail of loss.backward() through SpatialGenerator.layers
+ *                                      (building blocks of svae_step, exposed for tests)
  *
  * Conventions
  *   - plain C, no torch types: raw DEVICE pointers, sizes, a cudaStream_t passed as void*.
  *   - the caller owns every buffer (parameters, gradients, Adam state, inputs, outputs, workspace);
- *     the library never allocates device memory, never retains pointers, never synchronises:
- *     all work is enqueued on `stream` (CUDA-graph capturable).
+ *     the library never allocates device memory, never retains a caller pointer between calls and never
+ *     synchronises: all work is enqueued on `stream` (CUDA-graph capturable), on that stream only.
+ *   - process-wide state, all of it: (1) three environment switches read ONCE per process, for A/B comparisons:
+ *     SVAE_TC_CTA_GROUP=1 (single-CTA instead of CTA-pair tensor-core GEMMs), SVAE_RESID_TC=0 (ResidLinear networks
+ *     on the fp32 kernels in FAST precision), SVAE_CTF_FAST=1 (register-tiled CTF correlation); they select between
+ *     kernels that pass the same parity tests; (2) the per-kernel "max dynamic shared memory" attribute, set on a
+ *     kernel's first launch; (3) the launch counter behind svae_launch_count(); (4) the last error text per thread.
+ *   - accumulated outputs (gradient buffers, `+=` in the text below) are summed with fp32 atomics across thread
+ *     blocks: the summation ORDER, hence the last bits of a gradient, can differ between two runs on the same input
+ *     (|difference| ~ 1e-7 relative; the reference's cuBLAS split-K GEMMs behave the same way).
+ *   - svae_step / svae_decoder_* walk the minibatch in chunks of whole images sized so that the activation part of the
+ *     workspace stays near 6 GiB (cfg.chunk_images = 0) or in chunks of cfg.chunk_images; svae_workspace_bytes()
+ *     reports the size for that choice, results do not depend on it, and a workspace smaller than reported is
+ *     refused with SVAE_ENOSPACE (never silently re-chunked).
  *   - every entry returns 0 on success or a negative SVAE_E* code; svae_last_error() gives text.
  *   - there is NO CPU fallback: without a CUDA device the calls fail with SVAE_ECUDA.
  *   - tensors are row-major fp32 unless stated; weights use nn.Linear layout (out_features, in_features).

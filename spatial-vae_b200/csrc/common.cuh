@@ -108,8 +108,6 @@ struct TcExtra {
     int out_f32 = 0;
     // mode 0: ResidLinear (models.py:13-21): out = act(A W^T + bias + resid), resid (M x N, bf16, ld elements)
     const void* resid = nullptr; int ld_resid = 0;
-    // mode 1: per-image moments S[b0 + m/P, {1,x,y}, n] += out[m,n] * {1, grid[m%P]} instead of storing out
-    float* red_S = nullptr; int red_ld = 0; const float* red_grid = nullptr; int red_P = 0; int red_b0 = 0;
 };
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
             int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,

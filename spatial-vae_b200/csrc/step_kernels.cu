@@ -202,20 +202,25 @@ __global__ void __launch_bounds__(256) layer0_k(int P, int act, int b0, const fl
             const int lanes = max(1, 256 / groups);
             const int rl = threadIdx.x / groups;
             if (rl >= lanes) break;
-            float w0[8], w1[8], hb[8];
+            // column pairs in packed (f32x2) registers: half the FMA issue slots, the MUFU pipe (tanh) sets the pace
+            float2 w0[4], w1[4], hb[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int n = g * 8 + e;
-                const bool ok = n < H;
-                w0[e] = ok ? coord_w[n * 2 + 0] : 0.f;
-                w1[e] = ok ? coord_w[n * 2 + 1] : 0.f;
-                hb[e] = ok ? hz[(long)b * Hp + n] : 0.f;
+            for (int e = 0; e < 4; ++e) {
+                const int n = g * 8 + 2 * e;
+                w0[e].x = n < H ? coord_w[n * 2 + 0] : 0.f;         w0[e].y = n + 1 < H ? coord_w[n * 2 + 2] : 0.f;
+                w1[e].x = n < H ? coord_w[n * 2 + 1] : 0.f;         w1[e].y = n + 1 < H ? coord_w[n * 2 + 3] : 0.f;
+                hb[e].x = n < H ? hz[(long)b * Hp + n] : 0.f;       hb[e].y = n + 1 < H ? hz[(long)b * Hp + n + 1] : 0.f;
             }
+#pragma unroll 2
             for (int r = rl; r < nrows; r += lanes) {
-                const float x0 = sx[r][0], x1 = sx[r][1];
+                const float2 x0 = make_float2(sx[r][0], sx[r][0]), x1 = make_float2(sx[r][1], sx[r][1]);
                 float v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = act_apply<FAST>(act, fmaf(w0[e], x0, fmaf(w1[e], x1, hb[e])));
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a = __ffma2_rn(w0[e], x0, __ffma2_rn(w1[e], x1, hb[e]));
+                    v[2 * e] = act_apply<FAST>(act, a.x);
+                    v[2 * e + 1] = act_apply<FAST>(act, a.y);
+                }
                 store8(out + (long)r * Hp + g * 8, v);
             }
         }

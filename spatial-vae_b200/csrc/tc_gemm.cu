@@ -10,7 +10,6 @@
 //                 (+ optional fused output layer: o[m,c] += sum_n h[m,n] W_o[c,n])
 //                 (RES: ResidLinear, out = act(A W^T + bias + R) with the residual tile R streamed into the epilogue)
 //   mode 1  DX  : out[M,N]  = (A[M,K] W[K,N]) .* act'(aux[M,N])        A K-major,  B MN-major
-//                 (RED: instead of storing, reduce per image: S[b,{1,x,y},n] += sum_p out[b*P+p, n] {1,x_p,y_p})
 //   mode 2  DW  : outf[M,N] += A[Kr,M]^T Bm[Kr,N]  (split over Kr)     A MN-major, B MN-major
 #include "tc_ptx.cuh"
 
@@ -38,7 +37,7 @@ __host__ __device__ constexpr int stages_of(int cg, int mode) {
 }
 // shared-memory map after the operand ring:
 //   2 output staging blocks per epilogue group | (mode 1) 2 aux blocks per group |
-//   tables: mode 0: 2 x (bias[BN] + W_o[3][BN]) floats; mode 1 RED: 2 x (x[128], y[128], image[128]) | barriers
+//   tables: mode 0: 2 x (bias[BN] + W_o[3][BN]) floats | barriers
 __host__ __device__ constexpr int off_out_stage(int cg, int mode) { return stages_of(cg, mode) * stage_bytes(cg); }
 __host__ __device__ constexpr int off_aux_stage(int cg, int mode) {
     return off_out_stage(cg, mode) + (mode == 2 ? 0 : 2 * epi_groups(cg) * EPI_BLOCK_BYTES);
@@ -46,9 +45,8 @@ __host__ __device__ constexpr int off_aux_stage(int cg, int mode) {
 __host__ __device__ constexpr int off_tables(int cg, int mode) {
     return off_aux_stage(cg, mode) + ((mode == 1 || mode == LAYOUT_FWD_RES) ? 2 * epi_groups(cg) * EPI_BLOCK_BYTES : 0);
 }
-constexpr int RED_TABLE_BYTES = 128 * 8 + 128 * 2;    // (x,y) float2 per row + int16 image index per row
 __host__ __device__ constexpr int table_bytes(int mode) {
-    return (mode == 0 || mode == LAYOUT_FWD_RES) ? 2 * (1 + MAX_DOT_C) * BN * 4 : (mode == 1 ? 2 * RED_TABLE_BYTES : 0);
+    return (mode == 0 || mode == LAYOUT_FWD_RES) ? 2 * (1 + MAX_DOT_C) * BN * 4 : 0;
 }
 __host__ __device__ constexpr int off_bars(int cg, int mode) { return off_tables(cg, mode) + table_bytes(mode); }
 // The dynamic shared memory is declared 1024-byte aligned; the pair dX kernel has no room for alignment slack
@@ -73,8 +71,6 @@ struct TcParams {
     int res;                  // mode 0: a bf16 residual tile is added before the activation (ResidLinear)
     // mode 0, optional: fused output layer (models.py:84): o_accum[m, c] += sum_n h[m,n] * out_w[c, n]
     const float* out_w; int out_w_ld; int dot_c; float* o_accum;
-    // mode 1 RED: per-image moments of the result instead of storing it
-    float* red_S; int red_ld; const float* red_grid; int red_P; int red_b0;
 };
 
 // MODE: 0 fwd, 1 dX, 2 dW.  ACT: activation of the epilogue (compile time so the per-element code
@@ -82,9 +78,8 @@ struct TcParams {
 // CG: 1 = one CTA per 128 x 256 tile; 2 = CTA pair (cluster of 2, cta_group::2) per 256 x 256 tile.
 // OUT32: modes 0/1 write fp32 (and read an fp32 aux matrix) instead of bf16: used by the encoder, whose
 // fp32 GEMMs run as three bf16 MMAs on hi/lo splits of the operands (error-compensated, ~fp32 accuracy).
-// RED: mode 1 only: per-image column moments of the result instead of storing it.
 // RES: mode 0, bf16 only: out = act(acc + bias + R), R (M x N, bf16) streamed by TMA into the epilogue like dX's aux.
-template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED, bool RES = false>
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RES = false>
 __global__ void __launch_bounds__(num_threads(CG), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
@@ -123,7 +118,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (MODE != 2 && !RED) tma_prefetch_desc(&tmOut);
+        if (MODE != 2) tma_prefetch_desc(&tmOut);
         if (AUX) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) {
@@ -306,8 +301,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // per-tile tables, double buffered by tile parity (a fast group may already be one tile ahead)
                 float* s_bias = s_tab + par * (1 + MAX_DOT_C) * BN;
                 float* s_wo = s_bias + BN;
-                float2* s_xy = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_tab) + par * RED_TABLE_BYTES);
-                short* s_img = reinterpret_cast<short*>(s_xy + 128);
                 if (MODE == 0) {
                     for (int i = etid; i < BN; i += 128 * EG) {
                         const int n = nt * BN + i;
@@ -317,20 +310,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int c = 0; c < DOTC; ++c)
                                 s_wo[c * BN + i] = (n < p.bias_n) ? p.out_w[(size_t)c * p.out_w_ld + n] : 0.f;
                         }
-                    }
-                    epi_bar_sync_all(128 * EG);
-                }
-                if (RED) {
-                    for (int i = etid; i < 128; i += 128 * EG) {
-                        const int mr = m_cta + i;
-                        int img = -1; float cx = 0.f, cy = 0.f;
-                        if (mr < p.M) {
-                            img = mr / p.red_P;
-                            const int pp = mr - img * p.red_P;
-                            cx = __ldg(p.red_grid + 2 * pp); cy = __ldg(p.red_grid + 2 * pp + 1);
-                            img += p.red_b0;
-                        }
-                        s_xy[i] = make_float2(cx, cy); s_img[i] = (short)img;
                     }
                     epi_bar_sync_all(128 * EG);
                 }
@@ -348,7 +327,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint8_t* astage = aux_stage + buf * EPI_BLOCK_BYTES;
                     if (AUX) mbar_wait(auxfull_g + 8 * buf, (blk >> 1) & 1);
                     // the TMA store issued two blocks ago must have finished READING this staging buffer
-                    if (!RED && leader) tma_store_wait_read<1>();
+                    if (leader) tma_store_wait_read<1>();
                     epi_bar_sync(eg);
 #pragma unroll
                     for (int half = 0; half < HALVES; ++half) {
@@ -429,44 +408,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                         }
                     }
-                    if (!RED) fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
                     epi_bar_sync(eg);
                     if (leader) {
-                        if (!RED) {
-                            tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * BCOLS, m_cta);   // clips rows >= M
-                            tma_store_commit();
-                        }
+                        tma_store_2d(&tmOut, smem_u32(ostage), nt * BN + jb * BCOLS, m_cta);   // clips rows >= M
+                        tma_store_commit();
                         if (AUX) prefetch_aux();           // aux buffer `buf` is free again
-                    }
-                    if (RED) {
-                        // per-image moments of this 128 x 64 bf16 block: thread = (column pair, 32-row quarter)
-                        const int cp = gtid & 31, rq = gtid >> 5;
-                        const int n = nt * BN + jb * 64 + 2 * cp;
-                        const uint8_t* colp = ostage + (cp & 3) * 4;
-                        float s0 = 0.f, s1 = 0.f, x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
-                        int cur = -1;
-                        auto flush = [&]() {
-                            if (cur >= 0) {
-                                float* sp = p.red_S + (size_t)cur * 3 * p.red_ld + n;
-                                atomicAdd(sp, s0); atomicAdd(sp + 1, s1);
-                                atomicAdd(sp + p.red_ld, x0); atomicAdd(sp + p.red_ld + 1, x1);
-                                atomicAdd(sp + 2 * p.red_ld, y0); atomicAdd(sp + 2 * p.red_ld + 1, y1);
-                            }
-                            s0 = s1 = x0 = x1 = y0 = y1 = 0.f;
-                        };
-#pragma unroll 4
-                        for (int r = rq * 32; r < rq * 32 + 32; ++r) {
-                            const int img = s_img[r];
-                            if (img != cur) { flush(); cur = img; }
-                            const uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r * 128 + (((cp >> 2) ^ (r & 7)) << 4));
-                            const float d0 = __uint_as_float(w << 16), d1 = __uint_as_float(w & 0xffff0000u);
-                            const float2 xy = s_xy[r];
-                            const float cx = xy.x, cy = xy.y;
-                            s0 += d0; s1 += d1;
-                            x0 = fmaf(cx, d0, x0); x1 = fmaf(cx, d1, x1);
-                            y0 = fmaf(cy, d0, y0); y1 = fmaf(cy, d1, y1);
-                        }
-                        flush();
                     }
                 }
                 release_accumulator();
@@ -475,7 +422,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot[c]);
                 }
             }
-            if (!RED && leader) tma_store_wait_read<0>();
+            if (leader) tma_store_wait_read<0>();
         }
     }
 
@@ -489,12 +436,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side: launch plumbing ---------------------------------------------------------------------------
-template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RED, bool RES = false>
+template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RES = false>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x, const TcParams& p,
            int grid, cudaStream_t st) {
     static bool configured = false;
     constexpr int LM = RES ? LAYOUT_FWD_RES : MODE;
-    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG, OUT32, RED, RES>;
+    auto kern = tc_gemm_kernel<MODE, ACT, DOTC, CG, OUT32, RES>;
     if (!configured) {
         SVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(CG, LM)));
         configured = true;
@@ -520,22 +467,21 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, con
 template <int MODE, int ACT>
 int launch_variant(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
                    const TcParams& p, int cg, int grid, cudaStream_t st) {
-#define SVAE_TC_LAUNCH(M_, D_, O_, R_)                                                         \
-    (cg == 2 ? launch<M_, ACT, D_, 2, O_, R_>(a, b, o, x, p, grid, st)                          \
-             : launch<M_, ACT, D_, 1, O_, R_>(a, b, o, x, p, grid, st))
+#define SVAE_TC_LAUNCH(M_, D_, O_)                                                             \
+    (cg == 2 ? launch<M_, ACT, D_, 2, O_>(a, b, o, x, p, grid, st)                              \
+             : launch<M_, ACT, D_, 1, O_>(a, b, o, x, p, grid, st))
     if (MODE == 0) {
         if (p.res)
-            return cg == 2 ? launch<0, ACT, 0, 2, false, false, true>(a, b, o, x, p, grid, st)
-                           : launch<0, ACT, 0, 1, false, false, true>(a, b, o, x, p, grid, st);
-        if (p.out_f32) return SVAE_TC_LAUNCH(0, 0, true, false);
-        if (p.o_accum == nullptr) return SVAE_TC_LAUNCH(0, 0, false, false);
-        if (p.dot_c == 1) return SVAE_TC_LAUNCH(0, 1, false, false);
-        if (p.dot_c == 2) return SVAE_TC_LAUNCH(0, 2, false, false);
-        return SVAE_TC_LAUNCH(0, 3, false, false);
+            return cg == 2 ? launch<0, ACT, 0, 2, false, true>(a, b, o, x, p, grid, st)
+                           : launch<0, ACT, 0, 1, false, true>(a, b, o, x, p, grid, st);
+        if (p.out_f32) return SVAE_TC_LAUNCH(0, 0, true);
+        if (p.o_accum == nullptr) return SVAE_TC_LAUNCH(0, 0, false);
+        if (p.dot_c == 1) return SVAE_TC_LAUNCH(0, 1, false);
+        if (p.dot_c == 2) return SVAE_TC_LAUNCH(0, 2, false);
+        return SVAE_TC_LAUNCH(0, 3, false);
     }
-    if (p.out_f32) return SVAE_TC_LAUNCH(1, 0, true, false);
-    if (p.red_S != nullptr) return SVAE_TC_LAUNCH(1, 0, false, true);
-    return SVAE_TC_LAUNCH(1, 0, false, false);
+    if (p.out_f32) return SVAE_TC_LAUNCH(1, 0, true);
+    return SVAE_TC_LAUNCH(1, 0, false);
 #undef SVAE_TC_LAUNCH
 }
 
@@ -564,10 +510,7 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     p.out_w = ex.out_w; p.out_w_ld = ex.out_w_ld; p.dot_c = ex.dot_c; p.o_accum = ex.o_accum;
     p.out_f32 = (ex.out_f32 && mode != 2) ? 1 : 0;
     p.res = (mode == 0 && ex.resid != nullptr) ? 1 : 0;
-    p.red_S = (mode == 1) ? ex.red_S : nullptr; p.red_ld = ex.red_ld; p.red_grid = ex.red_grid;
-    p.red_P = ex.red_P; p.red_b0 = ex.red_b0;
     const bool f32 = p.out_f32 != 0;
-    const bool red = p.red_S != nullptr;
     const uint32_t ebox = f32 ? 32 : 64;          // epilogue block: 128 bytes of columns
     const int cg = cta_group_size();
     p.m_tiles = ceil_div(M, BM * cg);
@@ -595,11 +538,9 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     } else if (mode == 1) {
         SVAE_REQUIRE(N % 64 == 0 && K % 64 == 0, SVAE_EINVAL, "tc_gemm dx: N, K must be multiples of 64");
         SVAE_REQUIRE(aux != nullptr, SVAE_EINVAL, "tc_gemm dx: aux is required");
-        SVAE_REQUIRE(!(red && f32), SVAE_EINVAL, "tc_gemm dx: the fused reduction works on the bf16 path");
-        SVAE_REQUIRE(!red || (ex.red_grid != nullptr && ex.red_P > 0), SVAE_EINVAL, "tc_gemm dx: reduction needs the grid");
         SVAE_TRY(make_map(&ma, A, M, K, lda, 64, 128));
         SVAE_TRY(make_map(&mb, W, K, N, ldw, 64, 64));
-        if (!red) SVAE_TRY(make_map(&mo, out, M, N, ldo, ebox, 128, f32));
+        SVAE_TRY(make_map(&mo, out, M, N, ldo, ebox, 128, f32));
         SVAE_TRY(make_map(&mx, aux, M, N, ldaux, ebox, 128, f32));
     } else {
         // A: (K rows) x (lda cols) with M <= lda logical columns; Bm: (K rows) x (ldw cols), N <= ldw
@@ -618,8 +559,8 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     const int grid = (tiles < groups ? tiles : groups) * cg;
     if (mode == 0) return launch_act<0>(ma, mb, mo, mx, p, cg, grid, st);
     if (mode == 1) return launch_act<1>(ma, mb, mo, mx, p, cg, grid, st);
-    if (cg == 2) return launch<2, SVAE_ACT_TANH, 0, 2, false, false>(ma, mb, mo, mx, p, grid, st);
-    return launch<2, SVAE_ACT_TANH, 0, 1, false, false>(ma, mb, mo, mx, p, grid, st);
+    if (cg == 2) return launch<2, SVAE_ACT_TANH, 0, 2, false>(ma, mb, mo, mx, p, grid, st);
+    return launch<2, SVAE_ACT_TANH, 0, 1, false>(ma, mb, mo, mx, p, grid, st);
 }
 
 }  // namespace svae

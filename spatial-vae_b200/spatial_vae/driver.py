@@ -406,6 +406,22 @@ def export_batch_as_image(data, output, image_dims, channels_last=True):
     save_image(images.cpu(), output, nrow=int(data.size(0) ** 0.5), padding=3, pad_value=0.5)
 
 
+def sample_dump_hook(args, out_dir, epoch, image_dims, x_coord, p_net, q_net, rotate, translate, z_scale=1):
+    """first_batch_hook for run_epoch(train=False): every save_interval epochs the reference's eval_model writes the
+    first validation batch's reconstruction ({epoch}_{label}.png) and its decode on the un-rotated grid
+    ({epoch}_dis_{label}.png) under outputs_<prefix>/images (train_mnist.py:213-224, train_galaxy.py:280-293)."""
+    if out_dir is None or args.save_interval <= 0 or (epoch + 1) % args.save_interval != 0:
+        return None
+    label = save_label(args)
+
+    def hook(y, y_hat):
+        shown = minibatch_for_display(x_coord, y, p_net, q_net, rotate=rotate, translate=translate, z_scale=z_scale)
+        export_batch_as_image(shown, '{}/images/{}_dis_{}.png'.format(out_dir, epoch, label), image_dims)
+        export_batch_as_image(y_hat.detach().reshape(shown.shape), '{}/images/{}_{}.png'.format(out_dir, epoch, label),
+                              image_dims)
+    return hook
+
+
 def add_b200_flags(parser, hyphen=False):
     """Flags this build adds on top of the reference's."""
     sep = '-' if hyphen else '_'

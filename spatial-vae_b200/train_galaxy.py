@@ -123,7 +123,13 @@ def main(argv=None):
         images_val = np.load(args.test_path)
         if args.make_mono:      # only the training set is converted (reference train_galaxy.py:366-370)
             images_train = np.mean(images_train, axis=3)
-        np.random.shuffle(images_train)
+        # every data-parallel rank must hold the SAME dataset order (run_epoch hands each rank a slice of one shared
+        # permutation): shuffle with a seeded generator whenever there are several ranks or --seed is given; a single
+        # unseeded process shuffles with the global numpy RNG as the reference does (train_galaxy.py:372)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.seed is not None:
+            np.random.default_rng(args.seed if args.seed is not None else 0).shuffle(images_train)
+        else:
+            np.random.shuffle(images_train)
     if args.num_train_images > 0:
         images_train = images_train[:args.num_train_images]
         images_val = images_val[:args.num_train_images]
@@ -181,8 +187,10 @@ def main(argv=None):
         if rank == 0:
             print(line, flush=True)
         if len(y_val) > 0:
+            hook = D.sample_dump_hook(args, out_dir, epoch, (rows, cols), x_coord, p_net, q_net, rotate, translate,
+                                      z_scale) if rank == 0 else None
             e, err, kl = D.run_epoch(trainer, x_coord, y_val, train=False, minibatch_size=args.minibatch_size,
-                                     z_scale=z_scale)
+                                     z_scale=z_scale, first_batch_hook=hook)
             line = '\t'.join(map(str, [epoch, e, err, kl]))
             val_lines.append(line)
             if rank == 0:

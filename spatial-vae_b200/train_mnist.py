@@ -176,7 +176,9 @@ def main(argv=None):
         train_lines.append(line)
         if rank == 0:
             print(line, flush=True)
-        e, err, kl = D.run_epoch(trainer, x_coord, y_test, train=False, minibatch_size=args.minibatch_size)
+        hook = D.sample_dump_hook(args, out_dir, epoch, (n, m), x_coord, p_net, q_net, rotate, translate) if rank == 0 else None
+        e, err, kl = D.run_epoch(trainer, x_coord, y_test, train=False, minibatch_size=args.minibatch_size,
+                                 first_batch_hook=hook)
         line = '\t'.join(map(str, [epoch, e, err, kl]))
         val_lines.append(line)
         if rank == 0:
