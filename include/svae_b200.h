@@ -27,7 +27,7 @@
  *     synchronises: all work is enqueued on `stream` (CUDA-graph capturable), on that stream only.
  *   - process-wide state, all of it: (1) three environment switches read ONCE per process, for A/B comparisons:
  *     SVAE_TC_CTA_GROUP=1 (single-CTA instead of CTA-pair tensor-core GEMMs), SVAE_RESID_TC=0 (ResidLinear networks
- *     on the fp32 kernels in FAST precision), SVAE_CTF_FAST=1 (register-tiled CTF correlation); they select between
+ *     on the fp32 kernels in FAST precision), SVAE_CTF_FAST=0 (generic instead of register-tiled 39x39 CTF correlation); they select between
  *     kernels that pass the same parity tests; (2) the per-kernel "max dynamic shared memory" attribute, set on a
  *     kernel's first launch; (3) the launch counter behind svae_launch_count(); (4) the last error text per thread.
  *   - accumulated outputs (gradient buffers, `+=` in the text below) are summed with fp32 atomics across thread

@@ -159,6 +159,16 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     svae_emu::yield(svae_emu::WAIT_WARP);
     return r;
 }
+inline float __shfl_sync(unsigned, float v, int src_lane) {
+    svae_emu::State& s = svae_emu::state();
+    const int me = s.cur;
+    s.shfl[me] = v;
+    svae_emu::yield(svae_emu::WAIT_WARP);
+    const int partner = (me & ~31) | (src_lane & 31);
+    const float r = (partner < s.n) ? s.shfl[partner] : v;
+    svae_emu::yield(svae_emu::WAIT_WARP);
+    return r;
+}
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
