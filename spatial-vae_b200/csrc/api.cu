@@ -725,10 +725,6 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
                                        d.f(p.dlat), st));
             SVAE_TRY(latent_backward(s, c, nullptr, p.Hp, d.f(p.img), nullptr, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
                                      eps, d.f(p.g_zo), st, d.f(p.dlat)));
-        } else if (s.Z <= 256) {
-            SVAE_TRY(first_layer_backward_fused(s, c, d.f(p.S), p.Hp, d.f(p.img), d.f(p.zs), dp.coord_w,
-                                                s.Z > 0 ? dp.latent_w : nullptr, zo, eps, gd->coord_w, gd->coord_b,
-                                                gd->latent_w, d.f(p.g_zo), st));
         } else {
             SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
                                              s.Z > 0 ? d.f(p.dz) : nullptr, st));

@@ -71,13 +71,6 @@ int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int
                     const float* coord_w, const float* dz, const float* zo, const float* eps, float* g_zo,
                     cudaStream_t st, const float* coord_pre = nullptr);
 
-// Everything downstream of S on the default first layer in two launches: dWc, dbc, dWz (reduction over images) and
-// g_zo (per image: dz = z_scale Wz^T s_b, d theta, d dx, KL gradients).  zs: the scaled z (B, Z); latent_w may be NULL.
-int first_layer_backward_fused(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
-                               const float* zs, const float* coord_w, const float* latent_w, const float* zo,
-                               const float* eps, float* d_coord_w, float* d_coord_b, float* d_latent_w, float* g_zo,
-                               cudaStream_t st);
-
 // ---- decoder options (option_kernels.cu): --expand-coords (F = 5 coordinate features) and --bilinear (per-image
 // coordinate weights w[b*w_img_stride + n*F + i]; stride 0 = coord_linear.weight shared by all images).
 // Tm (B, F+1, Hp) are the feature moments of delta0 (see first_layer.cuh).

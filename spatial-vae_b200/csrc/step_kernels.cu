@@ -1020,167 +1020,6 @@ int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused consumers of the per-image first-layer sums S, default first layer (2 coordinate features):
-//   first_layer_reduce_k   over images:  dWc, dbc (coord_linear), dWz += S_s^T zs (latent_linear)
-//   latent_backward_fused_k per image:   dz = z_scale * Wz^T s_b, d theta, d dx, KL gradients -> g_zo (B, 2I)
-// They replace coord_param_grad + two thin sgemms + latent_backward (4 launches, ~65 us at C2) by 2 (~15 us).
-// ------------------------------------------------------------------------------------------------
-constexpr int FL_IMGS = 32;     // images staged per shared-memory tile of zs
-constexpr int FL_MAXJ = 8;      // latent columns per thread: Z <= 16 * FL_MAXJ = 128 per pass over the images
-
-__global__ void __launch_bounds__(256) first_layer_reduce_k(const float* __restrict__ S, const float* __restrict__ img,
-                                                            const float* __restrict__ zs, int B, int H, int Hp, int Z,
-                                                            float* __restrict__ dwc, float* __restrict__ dbc,
-                                                            float* __restrict__ dwz) {
-    extern __shared__ float zs_s[];                       // FL_IMGS x Z
-    __shared__ float img_s[FL_IMGS][4];
-    const int n = blockIdx.x * 16 + (threadIdx.x >> 4), jl = threadIdx.x & 15;
-    const int per = ceil_div(B, gridDim.y);
-    const int bs = blockIdx.y * per, be = min(B, bs + per);
-    const bool n_ok = n < H;
-    float a0 = 0.f, a1 = 0.f, ab = 0.f;
-    for (int jc = 0; jc < max(Z, 1); jc += 16 * FL_MAXJ) {
-        float acc[FL_MAXJ];
-#pragma unroll
-        for (int q = 0; q < FL_MAXJ; ++q) acc[q] = 0.f;
-        for (int b0 = bs; b0 < be; b0 += FL_IMGS) {
-            const int nb = min(FL_IMGS, be - b0);
-            __syncthreads();
-            for (int i = threadIdx.x; i < nb * Z; i += 256) zs_s[i] = zs[(long)b0 * Z + i];
-            if (threadIdx.x < nb * 4) img_s[threadIdx.x >> 2][threadIdx.x & 3] = img[(long)b0 * 4 + threadIdx.x];
-            __syncthreads();
-            if (!n_ok) continue;
-            for (int bl = 0; bl < nb; ++bl) {
-                const float* Sb = S + (long)(b0 + bl) * 3 * Hp;
-                const float sv = Sb[n];
-                if (jc == 0 && jl == 0) {
-                    const float m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
-                    const float cs = img_s[bl][0], sn = img_s[bl][1];
-                    ab += sv;
-                    a0 += cs * m0 - sn * m1 + img_s[bl][2] * sv;
-                    a1 += sn * m0 + cs * m1 + img_s[bl][3] * sv;
-                }
-#pragma unroll
-                for (int q = 0; q < FL_MAXJ; ++q) {
-                    const int j = jc + jl + 16 * q;
-                    if (j < Z) acc[q] = fmaf(sv, zs_s[bl * Z + j], acc[q]);
-                }
-            }
-        }
-        if (n_ok) {
-#pragma unroll
-            for (int q = 0; q < FL_MAXJ; ++q) {
-                const int j = jc + jl + 16 * q;
-                if (j < Z) atomicAdd(dwz + (long)n * Z + j, acc[q]);
-            }
-        }
-    }
-    if (n_ok && jl == 0) {
-        atomicAdd(dwc + n * 2, a0);
-        atomicAdd(dwc + n * 2 + 1, a1);
-        atomicAdd(dbc + n, ab);
-    }
-}
-
-constexpr int LB_MAXJ = 8;      // latent columns per lane: Z <= 256
-
-__global__ void __launch_bounds__(256) latent_backward_fused_k(SvaeShape s, SvaeConfig c, const float* __restrict__ S,
-                                                               int Hp, const float* __restrict__ img,
-                                                               const float* __restrict__ coord_w,
-                                                               const float* __restrict__ latent_w,
-                                                               const float* __restrict__ zo, const float* __restrict__ eps,
-                                                               float* __restrict__ g_zo) {
-    extern __shared__ float wz_s[];                       // 32 x Z tile of latent_linear.weight
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 8 + warp;
-    const bool live = b < s.B;
-    const int Z = s.Z;
-    const float* Sb = S + (long)(live ? b : 0) * 3 * Hp;
-    const float cs = live ? img[b * 4] : 0.f, sn = live ? img[b * 4 + 1] : 0.f;
-    float dth = 0.f, d0 = 0.f, d1 = 0.f, dz[LB_MAXJ];
-#pragma unroll
-    for (int q = 0; q < LB_MAXJ; ++q) dz[q] = 0.f;
-    for (int n0 = 0; n0 < s.H; n0 += 32) {
-        const int nn = min(32, s.H - n0);
-        __syncthreads();
-        if (latent_w != nullptr)
-            for (int i = threadIdx.x; i < nn * Z; i += 256) wz_s[i] = latent_w[(long)n0 * Z + i];
-        __syncthreads();
-        const int n = n0 + lane;
-        float sv = 0.f;
-        if (live && lane < nn) {
-            const float w0 = coord_w[n * 2], w1 = coord_w[n * 2 + 1];
-            const float m0 = Sb[Hp + n], m1 = Sb[2 * Hp + n];
-            sv = Sb[n];
-            dth = fmaf(w0, -sn * m0 - cs * m1, fmaf(w1, cs * m0 - sn * m1, dth));
-            d0 = fmaf(w0, sv, d0);
-            d1 = fmaf(w1, sv, d1);
-        }
-        if (latent_w != nullptr) {
-            for (int k = 0; k < nn; ++k) {
-                const float svk = __shfl_sync(0xffffffffu, sv, k);
-#pragma unroll
-                for (int q = 0; q < LB_MAXJ; ++q) {
-                    const int j = lane + 32 * q;
-                    if (j < Z) dz[q] = fmaf(svk, wz_s[k * Z + j], dz[q]);
-                }
-            }
-        }
-    }
-    dth = warp_sum(dth); d0 = warp_sum(d0); d1 = warp_sum(d1);
-    if (!live) return;                                    // whole warps only: b is per warp
-    const int I = s.I, rot = c.rotate ? 1 : 0, zcol = rot + (c.translate ? 2 : 0);
-    const float gs = c.grad_scale;
-    for (int q = 0; q * 32 < I; ++q) {                    // warp-uniform trip count: the shuffles below need every lane
-        const int i = lane + 32 * q;
-        // dz element j = i - zcol lives in lane j % 32, register j / 32
-        const int j = i - zcol;
-        float dzv = 0.f;
-#pragma unroll
-        for (int r = 0; r < LB_MAXJ; ++r) {
-            const float cand = __shfl_sync(0xffffffffu, dz[r], j & 31);
-            if (j >= 0 && (j >> 5) == r) dzv = cand;
-        }
-        if (i >= I) continue;
-        const float mu = zo[(long)b * 2 * I + i], ls = zo[(long)b * 2 * I + I + i];
-        const float sd = expf(ls);
-        float gl, kmu, kls;
-        if (rot && i == 0) {
-            gl = dth;
-            const float sp2 = c.theta_prior * c.theta_prior;
-            kmu = c.theta_kl_mean ? mu / sp2 : 0.f;
-            kls = -1.f + sd * sd / sp2;
-        } else {
-            if (i < zcol) gl = ((i - rot) == 0 ? d0 : d1) * c.dx_scale;
-            else gl = dzv * c.z_scale;
-            kmu = mu;
-            kls = -1.f + sd * sd;
-        }
-        g_zo[(long)b * 2 * I + i] = gl + gs * kmu;
-        g_zo[(long)b * 2 * I + I + i] = gl * sd * eps[(long)b * I + i] + gs * kls;
-    }
-}
-
-int first_layer_backward_fused(const SvaeShape& s, const SvaeConfig& c, const float* S, int Hp, const float* img,
-                               const float* zs, const float* coord_w, const float* latent_w, const float* zo,
-                               const float* eps, float* d_coord_w, float* d_coord_b, float* d_latent_w, float* g_zo,
-                               cudaStream_t st) {
-    if (s.B == 0) return SVAE_OK;
-    SVAE_REQUIRE(s.Z <= 32 * LB_MAXJ, SVAE_EINVAL, "fused first-layer backward supports z_dim <= %d", 32 * LB_MAXJ);
-    const int Zs = latent_w ? s.Z : 0;
-    {
-        dim3 g(ceil_div(s.H, 16), min(ceil_div(s.B, 64), 16));
-        const size_t smem = (size_t)FL_IMGS * (Zs > 0 ? Zs : 1) * sizeof(float);
-        first_layer_reduce_k<<<g, 256, smem, st>>>(S, img, zs, s.B, s.H, Hp, Zs, d_coord_w, d_coord_b, d_latent_w);
-        SVAE_LAUNCH_CHECK();
-    }
-    const size_t smem = (size_t)32 * (Zs > 0 ? Zs : 1) * sizeof(float);
-    latent_backward_fused_k<<<ceil_div(s.B, 8), 256, smem, st>>>(s, c, S, Hp, img, coord_w, latent_w, zo, eps, g_zo);
-    SVAE_LAUNCH_CHECK();
-    return SVAE_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, train_mnist.py:389-392,149-150), gather, fp32 -> padded bf16
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
