@@ -35,7 +35,10 @@ constexpr int DR_TILE_R = 256;               // pixel rows per tile (MMA N; each
 constexpr int DR_SLAB_BYTES = 8 * OP_BYTES;  // resident weight slab: 128 columns x 512 reduction elements
 constexpr int DR_TABLE_BYTES = DR_TILE_R * 8;      // per row pair: (g0, g0') and (g1, g1') as two float2 arrays
 
-__host__ __device__ constexpr int dr_stages(bool resident) { return resident ? 4 : 6; }
+#ifndef DR_STAGES_RES
+#define DR_STAGES_RES 4
+#endif
+__host__ __device__ constexpr int dr_stages(bool resident) { return resident ? DR_STAGES_RES : 6; }
 __host__ __device__ constexpr int dr_stage_bytes(bool resident) { return resident ? OP_BYTES : 2 * OP_BYTES; }
 __host__ __device__ constexpr int dr_off_ring(bool resident) { return resident ? DR_SLAB_BYTES : 0; }
 __host__ __device__ constexpr int dr_off_table(bool resident) {

@@ -21,11 +21,20 @@ constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 rows (or 128 M-columns) x 64 K
 constexpr int BOX_BYTES = 64 * 64 * 2;       // one 64x64 bf16 TMA box (MN-major operands)
 constexpr int MAX_DOT_C = 3;                  // output channels the fused output-layer dot supports
+#ifndef TC_STAGES_WIDE
+#define TC_STAGES_WIDE 4
+#endif
 constexpr int EPI_BLOCK_BYTES = 128 * 128;    // one 128-row x 128-byte epilogue block (SWIZZLE_128B)
-// Epilogue warp-groups per CTA.  Two groups were measured (round 1): no gain for fwd (the pair kernel is bound
-// by L2->SM operand bandwidth, not by epilogue latency) and they cost dX one ring stage, so one group is used.
-__host__ __device__ constexpr int epi_groups(int cg) { return (void)cg, 1; }
-__host__ __device__ constexpr int num_threads(int cg) { return 128 + 128 * epi_groups(cg); }
+// Epilogue warp-groups per CTA (TC_FWD_EPI_GROUPS, forward pair kernel only).  Two groups were measured in rounds 1
+// and 2 (fwd at C2: 397 us against 385-390 us with one group), as was a 5-stage operand ring (TC_STAGES_WIDE: 385 vs
+// 390 us) and an L2-resident problem (same TFLOP/s): the kernel is bound by neither epilogue latency, nor TMA
+// latency, nor HBM -- it sits at 80 % of what cuBLAS sustains under the 1 kW power cap -- so one group and four
+// stages, the configuration validated on hardware, are kept.
+#ifndef TC_FWD_EPI_GROUPS
+#define TC_FWD_EPI_GROUPS 1
+#endif
+__host__ __device__ constexpr int epi_groups(int cg, int mode) { return (cg == 2 && mode == 0) ? TC_FWD_EPI_GROUPS : 1; }
+__host__ __device__ constexpr int num_threads(int cg, int mode) { return 128 + 128 * epi_groups(cg, mode); }
 __host__ __device__ constexpr int b_stage_bytes(int cg) { return (BN / cg) * BK * 2; }        // 32 KB | 16 KB
 __host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b_stage_bytes(cg); }
 // Layout index of a kernel variant: its MODE, or 3 for the forward GEMM with a residual stream (mode 0 + the aux
@@ -33,17 +42,17 @@ __host__ __device__ constexpr int stage_bytes(int cg) { return A_STAGE_BYTES + b
 constexpr int LAYOUT_FWD_RES = 3;
 // ring depth: whatever the staging blocks leave (mode 1 needs aux blocks too)
 __host__ __device__ constexpr int stages_of(int cg, int mode) {
-    return cg == 2 ? ((mode == 1 && epi_groups(cg) == 2) ? 3 : 4) : 3;
+    return cg == 2 ? ((mode == 0 || mode == 2) ? TC_STAGES_WIDE : 4) : 3;
 }
 // shared-memory map after the operand ring:
 //   2 output staging blocks per epilogue group | (mode 1) 2 aux blocks per group |
 //   tables: mode 0: 2 x (bias[BN] + W_o[3][BN]) floats | barriers
 __host__ __device__ constexpr int off_out_stage(int cg, int mode) { return stages_of(cg, mode) * stage_bytes(cg); }
 __host__ __device__ constexpr int off_aux_stage(int cg, int mode) {
-    return off_out_stage(cg, mode) + (mode == 2 ? 0 : 2 * epi_groups(cg) * EPI_BLOCK_BYTES);
+    return off_out_stage(cg, mode) + (mode == 2 ? 0 : 2 * epi_groups(cg, mode) * EPI_BLOCK_BYTES);
 }
 __host__ __device__ constexpr int off_tables(int cg, int mode) {
-    return off_aux_stage(cg, mode) + ((mode == 1 || mode == LAYOUT_FWD_RES) ? 2 * epi_groups(cg) * EPI_BLOCK_BYTES : 0);
+    return off_aux_stage(cg, mode) + ((mode == 1 || mode == LAYOUT_FWD_RES) ? 2 * epi_groups(cg, mode) * EPI_BLOCK_BYTES : 0);
 }
 __host__ __device__ constexpr int table_bytes(int mode) {
     return (mode == 0 || mode == LAYOUT_FWD_RES) ? 2 * (1 + MAX_DOT_C) * BN * 4 : 0;
@@ -52,7 +61,7 @@ __host__ __device__ constexpr int off_bars(int cg, int mode) { return off_tables
 // The dynamic shared memory is declared 1024-byte aligned; the pair dX kernel has no room for alignment slack
 // (it traps if the base ever comes back misaligned), the others keep 1 KB of slack and align by hand.
 __host__ __device__ constexpr int align_slack(int cg, int mode) {
-    return (cg == 2 && mode == 1 && epi_groups(cg) == 2) ? 0 : 1024;
+    return (cg == 2 && mode == 1 && epi_groups(cg, mode) == 2) ? 0 : 1024;
 }
 __host__ __device__ constexpr int smem_bytes(int cg, int mode) { return off_bars(cg, mode) + 256 + align_slack(cg, mode); }
 static_assert(smem_bytes(1, 0) <= 232448 && smem_bytes(1, 1) <= 232448 && smem_bytes(2, 0) <= 232448 &&
@@ -80,7 +89,7 @@ struct TcParams {
 // fp32 GEMMs run as three bf16 MMAs on hi/lo splits of the operands (error-compensated, ~fp32 accuracy).
 // RES: mode 0, bf16 only: out = act(acc + bias + R), R (M x N, bf16) streamed by TMA into the epilogue like dX's aux.
 template <int MODE, int ACT, int DOTC, int CG, bool OUT32, bool RES = false>
-__global__ void __launch_bounds__(num_threads(CG), 1)
+__global__ void __launch_bounds__(num_threads(CG, RES ? LAYOUT_FWD_RES : MODE), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const TcParams p) {
     static_assert(!RES || (MODE == 0 && !OUT32 && DOTC == 0), "the residual stream exists for the plain bf16 forward");
@@ -91,8 +100,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int STAGE_BYTES = stage_bytes(CG);
     constexpr int BN_CTA = BN / CG;                // B-tile rows (N) staged by this CTA
     constexpr int TILE_M = BM * CG;                // rows of the output tile computed by the CTA (pair)
-    constexpr int EG = epi_groups(CG);             // epilogue warp-groups (4 warps each)
-    constexpr int NT = num_threads(CG);
+    constexpr int EG = epi_groups(CG, LM);         // epilogue warp-groups (4 warps each)
+    constexpr int NT = num_threads(CG, LM);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles (same offset in both CTAs of a pair)
@@ -448,7 +457,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, con
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(num_threads(CG));
+    cfg.blockDim = dim3(num_threads(CG, LM));
     cfg.dynamicSmemBytes = smem_bytes(CG, LM);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
