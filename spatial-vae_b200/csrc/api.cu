@@ -57,6 +57,56 @@ static size_t take(size_t& cur, size_t bytes) {
     return off;
 }
 
+// ---- side stream: independent SMALL kernels of the backward tail run next to each other -------------------------------
+// The tail of a step (first-layer parameter gradients, the encoder's dW / dX GEMMs and bias sums) is a chain of ~25
+// kernels with grids of 16-128 CTAs on a 148-SM device; half of them are independent of each other.  They are forked
+// onto one auxiliary stream per host thread and device (created on first use, kept for the life of the process;
+// non-blocking) with a fork / join event pair, so eager launches overlap and a captured CUDA graph gets parallel
+// branches.  The join happens before svae_step returns: nothing is left running on the auxiliary stream.
+// SVAE_SIDE_STREAM=0 keeps everything on the caller's stream (A/B comparisons; read once per process).
+struct Side {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool forked = false;
+};
+static bool side_stream_enabled() {
+    static const bool on = !(getenv("SVAE_SIDE_STREAM") != nullptr && getenv("SVAE_SIDE_STREAM")[0] == '0');
+    return on;
+}
+static int side_get(Side** out) {
+    static thread_local Side table[16];
+    *out = nullptr;
+    if (!side_stream_enabled()) return SVAE_OK;
+    int dev = 0;
+    SVAE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return SVAE_OK;
+    Side& s = table[dev];
+    if (s.aux == nullptr) {
+        SVAE_CUDA(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+        SVAE_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        SVAE_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    s.forked = false;
+    *out = &s;
+    return SVAE_OK;
+}
+// everything enqueued on `st` so far is visible to work enqueued on the auxiliary stream from here on
+static int side_fork(Side* s, cudaStream_t st) {
+    if (s == nullptr) return SVAE_OK;
+    SVAE_CUDA(cudaEventRecord(s->fork, st));
+    SVAE_CUDA(cudaStreamWaitEvent(s->aux, s->fork, 0));
+    s->forked = true;
+    return SVAE_OK;
+}
+// `st` waits for everything enqueued on the auxiliary stream so far
+static int side_join(Side* s, cudaStream_t st) {
+    if (s == nullptr || !s->forked) return SVAE_OK;
+    SVAE_CUDA(cudaEventRecord(s->join, s->aux));
+    SVAE_CUDA(cudaStreamWaitEvent(st, s->join, 0));
+    return SVAE_OK;
+}
+static cudaStream_t side_or(Side* s, cudaStream_t st) { return s != nullptr ? s->aux : st; }
+
 static int validate(const SvaeShape& s, const SvaeConfig& c) {
     SVAE_REQUIRE(s.B >= 0 && s.P > 0 && s.H > 0 && s.L >= 1 && s.L <= SVAE_MAX_LAYERS, SVAE_EINVAL,
                  "bad shape: B=%d P=%d H=%d L=%d", s.B, s.P, s.H, s.L);
@@ -219,6 +269,7 @@ static int encoder_forward_impl(const SvaeShape& s, int act, const SvaeEncoderPa
 // built from hi/lo splits of both operands (split3), fp32 accumulate, fp32 output.
 struct EncTc {
     const SvaeShape* s; const Plan* p; char* ws; cudaStream_t st;
+    Side* side = nullptr;      // independent dW / bias work of the backward goes to the auxiliary stream
     // weight of hidden layer l as the GEMMs see it: W_l, or an fp32 copy of W_l + I for a ResidLinear layer (l >= 1)
     int weight(const SvaeEncoderParams& q, int l, const float** w) const {
         *w = q.w[l];
@@ -262,16 +313,20 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
     const int Hqp = e.Hqp();
     const size_t wide = (size_t)(Hqp > 2 * s.I ? Hqp : 2 * s.I);
     float* buf[2] = {scratch, scratch + (size_t)s.B * wide};
+    // Two chains per layer: dW / db (reads g and the layer input, accumulates into the gradient buffers) on the
+    // auxiliary stream, the dX GEMM that produces the next g on the caller's stream.
+    cudaStream_t sw = side_or(e.side, e.st);
     // head (2I x Hq): fp32 FFMA
     const float* a_top = e.acts(s.Lq - 1);
+    SVAE_TRY(side_fork(e.side, e.st));
     SgemmArgs w{};
     w.A = g_out; w.sAm = 1; w.sAk = 2 * s.I;
     w.B = a_top; w.sBk = Hqp; w.sBn = 1;
     w.C = gq.w[s.Lq]; w.ldc = s.Hq;
     w.M = 2 * s.I; w.N = s.Hq; w.K = s.B;
     w.accumulate = 1; w.split_k = s.B >= 512 ? 8 : (s.B >= 128 ? 2 : 1);
-    SVAE_TRY(sgemm(w, e.st));
-    SVAE_TRY(col_sum<float>(g_out, s.B, 2 * s.I, 2 * s.I, gq.b[s.Lq], e.st));
+    SVAE_TRY(sgemm(w, sw));
+    SVAE_TRY(col_sum<float>(g_out, s.B, 2 * s.I, 2 * s.I, gq.b[s.Lq], sw));
     SgemmArgs d{};
     d.A = g_out; d.sAm = 2 * s.I; d.sAk = 1;
     d.B = q.w[s.Lq]; d.sBk = s.Hq; d.sBn = 1;
@@ -285,12 +340,14 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
         const float* a_in = (l == 0) ? x : e.acts(l - 1);
         const int k_in = e.kin(l), kinp = e.kinp(l);
         const long ld_in = (l == 0) ? k_in : Hqp;
+        // the auxiliary stream sees g (just produced on the caller's stream) ...
+        SVAE_TRY(side_fork(e.side, e.st));
         // dW_l (Hq, k_in) += g^T a_in : terms stacked along the reduction dimension (rows)
-        SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->gs_r), s.B, Hqp, 0, 0, e.st));
-        SVAE_TRY(split3(a_in, s.B, k_in, ld_in, e.b16(e.p->as_r), s.B, kinp, 0, 1, e.st));
+        SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->gs_r), s.B, Hqp, 0, 0, sw));
+        SVAE_TRY(split3(a_in, s.B, k_in, ld_in, e.b16(e.p->as_r), s.B, kinp, 0, 1, sw));
         SVAE_TRY(tc_gemm(2, s.Hq, k_in, 3 * s.B, e.b16(e.p->gs_r), Hqp, e.b16(e.p->as_r), kinp, nullptr, 0, nullptr, 0, -1,
-                         gq.w[l], k_in, e.st));
-        SVAE_TRY(col_sum<float>(g, s.B, s.Hq, Hqp, gq.b[l], e.st));
+                         gq.w[l], k_in, sw));
+        SVAE_TRY(col_sum<float>(g, s.B, s.Hq, Hqp, gq.b[l], sw));
         if (l == 0) break;
         // g_in (B, Hq) = (g W_l) .* act'(a_in)
         SVAE_TRY(split3(g, s.B, s.Hq, Hqp, e.b16(e.p->xs_k), s.B, Hqp, 1, 0, e.st));
@@ -302,6 +359,9 @@ static int encoder_backward_tc(const EncTc& e, int act, const SvaeEncoderParams&
         f32out.out_f32 = 1;
         SVAE_TRY(tc_gemm(1, s.B, kinp, 3 * Hqp, e.b16(e.p->xs_k), 3 * Hqp, e.b16(e.p->ws_r[l]), kinp, nullptr, 0, a_in,
                          Hqp, act, buf[cur], Hqp, e.st, f32out));
+        // ... and must be done reading it (and its split buffers) before the NEXT layer's dX overwrites the other
+        // ping-pong buffer's predecessor: join here keeps the two chains one layer apart at most
+        SVAE_TRY(side_join(e.side, e.st));
         g = buf[cur];
     }
     return SVAE_OK;
@@ -647,9 +707,13 @@ static int first_layer_param_grads_opt(const SvaeShape& s, const SvaeConfig& c, 
 static int first_layer_param_grads(const SvaeShape& s, const SvaeConfig& c, const Plan& p,
                                    const SvaeDecoderParams& dp, SvaeDecoderParams& g, const float* S,
                                    const float* img, const float* zs, float z_scale, int explicit_x, float* dz,
-                                   cudaStream_t st) {
+                                   cudaStream_t st_main, Side* side = nullptr) {
     (void)c;
     if (s.B == 0) return SVAE_OK;
+    // parameter gradients (accumulated, consumed by Adam only) on the auxiliary stream; dz, which the latent
+    // backward waits for, on the caller's
+    SVAE_TRY(side_fork(side, st_main));
+    cudaStream_t st = side_or(side, st_main);
     SVAE_TRY(coord_param_grad(S, img, s.B, s.H, p.Hp, explicit_x, g.coord_w, g.coord_b, st));
     if (s.Z > 0 && dp.latent_w != nullptr) {
         // dWz (H,Z) += S_s^T zs
@@ -670,10 +734,10 @@ static int first_layer_param_grads(const SvaeShape& s, const SvaeConfig& c, cons
             x.M = s.B; x.N = s.Z; x.K = s.H;
             x.alpha = z_scale;
             if (s.H >= 256) {      // narrow output, long K: split-K (see encoder_head_forward)
-                SVAE_CUDA(cudaMemsetAsync(dz, 0, (size_t)s.B * s.Z * sizeof(float), st));
+                SVAE_CUDA(cudaMemsetAsync(dz, 0, (size_t)s.B * s.Z * sizeof(float), st_main));
                 x.split_k = 4;
             }
-            SVAE_TRY(sgemm(x, st));
+            SVAE_TRY(sgemm(x, st_main));
         }
     }
     return SVAE_OK;
@@ -715,6 +779,8 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
                             dc.st));
         if (train) SVAE_TRY(decoder_chunk_backward<T>(dc, dp, *gd, b0, nb, in.grid, nullptr, nullptr));
     }
+    Side* side = nullptr;
+    if (train && (kFast || p.tc3)) SVAE_TRY(side_get(&side));
     finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
     SVAE_LAUNCH_CHECK();
     if (train) {
@@ -727,16 +793,18 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
                                      eps, d.f(p.g_zo), st, d.f(p.dlat)));
         } else {
             SVAE_TRY(first_layer_param_grads(s, c, p, dp, *gd, d.f(p.S), d.f(p.img), d.f(p.zs), c.z_scale, 0,
-                                             s.Z > 0 ? d.f(p.dz) : nullptr, st));
+                                             s.Z > 0 ? d.f(p.dz) : nullptr, st, side));
             SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
                                      eps, d.f(p.g_zo), st));
         }
         if (gq) {
+            enc_tc.side = side;
             if (enc_on_tc) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));
             else SVAE_TRY(encoder_backward_impl(s, c.activation, qp, x_enc, d.f(p.enc_acts), d.f(p.g_zo), *gq, nullptr,
                                                 d.f(p.enc_scratch), st, c.resid != 0));
         }
     }
+    SVAE_TRY(side_join(side, st));      // nothing is left running on the auxiliary stream
     return SVAE_OK;
 }
 

@@ -91,7 +91,8 @@ def test_bench_flop_model_matches_survey_table():
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """`bench.py --impl reference` (the CPU port of the reference step) needs no GPU and prints the contract's line."""
+    """`bench.py --impl reference` needs no GPU and prints the contract's line: the unmodified reference when
+    baseline/_ref exists (oracle/make_ref.py copies it where /root/reference is present), else the oracle port."""
     import json
     import subprocess
     root = os.path.dirname(PKG)
@@ -102,7 +103,9 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    have_ref = os.path.isdir(os.path.join(root, "baseline", "_ref", "spatial_vae"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["images_per_step"] == 100          # C1 runs at its real minibatch on the CPU
 
 
 def test_particle_preprocessing_matches_reference_recipes(tmp_path):
