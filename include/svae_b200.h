@@ -24,12 +24,16 @@
  *   - plain C, no torch types: raw DEVICE pointers, sizes, a cudaStream_t passed as void*.
  *   - the caller owns every buffer (parameters, gradients, Adam state, inputs, outputs, workspace);
  *     the library never allocates device memory, never retains a caller pointer between calls and never
- *     synchronises: all work is enqueued on `stream` (CUDA-graph capturable), on that stream only.
- *   - process-wide state, all of it: (1) three environment switches read ONCE per process, for A/B comparisons:
+ *     synchronises: all work is enqueued on `stream` (CUDA-graph capturable) or forked from and joined back to it (5).
+ *   - process-wide state, all of it: (1) four environment switches read ONCE per process, for A/B comparisons:
  *     SVAE_TC_CTA_GROUP=1 (single-CTA instead of CTA-pair tensor-core GEMMs), SVAE_RESID_TC=0 (ResidLinear networks
- *     on the fp32 kernels in FAST precision), SVAE_CTF_FAST=0 (generic instead of register-tiled 39x39 CTF correlation); they select between
- *     kernels that pass the same parity tests; (2) the per-kernel "max dynamic shared memory" attribute, set on a
- *     kernel's first launch; (3) the launch counter behind svae_launch_count(); (4) the last error text per thread.
+ *     on the fp32 kernels in FAST precision), SVAE_CTF_FAST=0 (generic instead of register-tiled 39x39 CTF
+ *     correlation), SVAE_SIDE_STREAM=0 (see 5); they select between kernels / schedules that pass the same parity
+ *     tests; (2) the per-kernel "max dynamic shared memory" attribute, set on a kernel's first launch; (3) the launch counter behind svae_launch_count(); (4) the last error text per thread;
+ *     (5) ONE auxiliary non-blocking stream and two events per host thread and device, created on the first training
+ *     call of svae_step: independent small kernels of the backward tail (parameter-gradient chains) are forked onto
+ *     it and joined back onto `stream` before the call returns, so nothing is left running there and a captured CUDA
+ *     graph simply gets parallel branches.
  *   - accumulated outputs (gradient buffers, `+=` in the text below) are summed with fp32 atomics across thread
  *     blocks: the summation ORDER, hence the last bits of a gradient, can differ between two runs on the same input
  *     (|difference| ~ 1e-7 relative; the reference's cuBLAS split-K GEMMs behave the same way).
