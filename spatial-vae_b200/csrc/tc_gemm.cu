@@ -326,9 +326,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 const int nblk = blocks_in_tile(tile);
-                float dot[DOTC > 0 ? DOTC : 1];
+                float2 dot2[DOTC > 0 ? DOTC : 1];          // even / odd column partial sums of the fused output dot
 #pragma unroll
-                for (int c = 0; c < (DOTC > 0 ? DOTC : 1); ++c) dot[c] = 0.f;
+                for (int c = 0; c < (DOTC > 0 ? DOTC : 1); ++c) dot2[c] = make_float2(0.f, 0.f);
 #pragma unroll 1
                 for (int jb = eg; jb < nblk; jb += EG, ++blk) {
                     const uint32_t buf = blk & 1;
@@ -386,18 +386,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         bv.x += __low2float(r01); bv.y += __high2float(r01);
                                         bv.z += __low2float(r23); bv.w += __high2float(r23);
                                     }
-                                    const float hh[4] = {
-                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 0]) + bv.x),
-                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 1]) + bv.y),
-                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 2]) + bv.z),
-                                        act_const<ACT>(__uint_as_float(v[4 * j4 + 3]) + bv.w)};
-                                    packed[2 * j4] = pack_bf16(hh[0], hh[1]);
-                                    packed[2 * j4 + 1] = pack_bf16(hh[2], hh[3]);
+                                    // packed f32x2 arithmetic: half the issue slots for the bias add and the output dot
+                                    const float2 a01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j4 + 0]), __uint_as_float(v[4 * j4 + 1])),
+                                                                  make_float2(bv.x, bv.y));
+                                    const float2 a23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])),
+                                                                  make_float2(bv.z, bv.w));
+                                    const float2 h01 = make_float2(act_const<ACT>(a01.x), act_const<ACT>(a01.y));
+                                    const float2 h23 = make_float2(act_const<ACT>(a23.x), act_const<ACT>(a23.y));
+                                    packed[2 * j4] = pack_bf16(h01.x, h01.y);
+                                    packed[2 * j4 + 1] = pack_bf16(h23.x, h23.y);
                                     if (fuse_dot) {
 #pragma unroll
                                         for (int c = 0; c < DOTC; ++c) {
                                             const float4 wv = *reinterpret_cast<const float4*>(s_wo + c * BN + tc + 4 * j4);
-                                            dot[c] = fmaf(hh[0], wv.x, fmaf(hh[1], wv.y, fmaf(hh[2], wv.z, fmaf(hh[3], wv.w, dot[c]))));
+                                            dot2[c] = __ffma2_rn(h01, make_float2(wv.x, wv.y),
+                                                                 __ffma2_rn(h23, make_float2(wv.z, wv.w), dot2[c]));
                                         }
                                     }
                                 }
@@ -428,7 +431,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 release_accumulator();
                 if (fuse_dot && m < p.M) {
 #pragma unroll
-                    for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot[c]);
+                    for (int c = 0; c < DOTC; ++c) atomicAdd(p.o_accum + (size_t)m * DOTC + c, dot2[c].x + dot2[c].y);
                 }
             }
             if (leader) tma_store_wait_read<0>();
