@@ -339,6 +339,8 @@ def init_distributed(device):
     import torch.distributed as dist
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
+        import atexit
+        atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
     return dist.get_rank() if dist.is_initialized() else 0
 
 
