@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/.."
 for sms in 148 4; do
   echo "== tcgen05 GEMM unit tests, $sms emulated SMs"
-  SVAE_EMU_SMS=$sms SVAE_TEST_BACKEND=emu python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "tc_gemm and not 78400"
+  SVAE_EMU_SMS=$sms SVAE_TEST_BACKEND=emu python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "tc_ and not 78400"
 done
 echo "== emulated step / fuzz suites, threads scheduled by index and in two pseudo-random orders"
 python -m pytest tests/test_emu_step.py tests/test_emu_fuzz.py -q -x -p no:cacheprovider

@@ -38,7 +38,7 @@ import pytest  # noqa: E402
 
 @pytest.mark.parametrize("sms,cta_group", [("4", "2"), ("3", "1")])
 def test_tcgen05_gemm_persistent_paths_on_a_small_emulated_device(sms, cta_group):
-    """The tcgen05 GEMM unit tests again on an emulated device with only a few SMs, so that every persistent CTA
+    """The tcgen05 GEMM unit tests (tc_gemm.cu and the fused backward kernels of tc_bwd.cu) again on an emulated device with only a few SMs, so that every persistent CTA
     (pair) walks several tiles: accumulator double buffering, ring wrap-around and mbarrier phase flips are exercised
     (a wrong arrival count or a missing phase flip deadlocks here and the scheduler aborts with the waiters listed).
     cta_group 2 = CTA pairs (the default), 1 = the single-CTA variant (SVAE_TC_CTA_GROUP=1)."""
@@ -46,7 +46,7 @@ def test_tcgen05_gemm_persistent_paths_on_a_small_emulated_device(sms, cta_group
     build()
     env = dict(os.environ, SVAE_TEST_BACKEND="emu", SVAE_EMU_SMS=sms, SVAE_TC_CTA_GROUP=cta_group)
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-           "-k", "tc_gemm and not 78400"]
+           "-k", "tc_ and not 78400"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
