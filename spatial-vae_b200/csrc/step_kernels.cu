@@ -812,8 +812,8 @@ __global__ void __launch_bounds__(256) col_sum_k(const T* __restrict__ src, int 
         if (pr * 2 + 1 < H) atomicAdd(dst + pr * 2 + 1, a1);
     }
 }
-// Wide variant (Hp % 8 == 0, Hp <= 2048): thread = (8-column group, row lane), 16-byte loads, four rows in flight per
-// thread.  The 4-byte-per-thread kernel above ran at 2.2 TB/s on the (524288 x 1024) bf16 delta matrices of C4
+// Wide variant (Hp % 8 == 0, Hp >= 256): thread = (8-column group, row lane), 16-byte loads, four rows in flight per
+// thread, 256 column groups per pass.  The 4-byte-per-thread kernel above ran at 2.2 TB/s on the (524288 x 1024) bf16 delta matrices of C4
 // (490 us each, two per step).
 template <typename T>
 __global__ void __launch_bounds__(256) col_sum_v8_k(const T* __restrict__ src, int rows, int H, int Hp,
@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(256) col_sum_v8_k(const T* __restrict__ src, i
 
 template <typename T>
 int col_sum(const T* src, int rows, int H, int Hp, float* dst, cudaStream_t st) {
-    if ((Hp & 7) == 0 && Hp >= 256 && Hp <= 2048 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    if ((Hp & 7) == 0 && Hp >= 256 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int rpb = rows >= 148 * 8 * 512 ? 512 : max(32, ceil_div(rows, 148 * 4));
         col_sum_v8_k<T><<<ceil_div(rows, rpb), 256, 0, st>>>(src, rows, H, Hp, dst, rpb);
         SVAE_LAUNCH_CHECK();
@@ -1088,19 +1088,37 @@ int latent_backward(const SvaeShape& s, const SvaeConfig& c, const float* S, int
 // ------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, train_mnist.py:389-392,149-150), gather, fp32 -> padded bf16
 // ------------------------------------------------------------------------------------------------
-__global__ void adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       size_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, int zero_grad,
-                       const float* __restrict__ bc_dev) {
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float lr, float b1, float b2, float eps,
+                                         float bc1, float bc2_sqrt, int zero_grad) {
+    const float gi = g;
+    const float mi = b1 * m + (1.f - b1) * gi;
+    const float vi = b2 * v + (1.f - b2) * gi * gi;
+    m = mi; v = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p -= (lr / bc1) * (mi / denom);
+    if (zero_grad) g = 0.f;
+}
+// 28 bytes of traffic per parameter: four elements per thread with 16-byte accesses (the flat buffers are 16-byte
+// aligned; the scalar version ran at 3.9 TB/s on the 89.7 M parameters of C4), scalar tail
+__global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
+                                              float bc1, float bc2_sqrt, int zero_grad, const float* __restrict__ bc_dev,
+                                              int vec) {
     if (bc_dev != nullptr) { bc1 = bc_dev[0]; bc2_sqrt = bc_dev[1]; }   // CUDA-graph replays: step-dependent scalars live in memory
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= (lr / bc1) * (mi / denom);
-        if (zero_grad) g[i] = 0.f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t i = tid; i < n4; i += nthreads) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        adam_one(pp.x, gg.x, mm.x, vv.x, lr, b1, b2, eps, bc1, bc2_sqrt, zero_grad);
+        adam_one(pp.y, gg.y, mm.y, vv.y, lr, b1, b2, eps, bc1, bc2_sqrt, zero_grad);
+        adam_one(pp.z, gg.z, mm.z, vv.z, lr, b1, b2, eps, bc1, bc2_sqrt, zero_grad);
+        adam_one(pp.w, gg.w, mm.w, vv.w, lr, b1, b2, eps, bc1, bc2_sqrt, zero_grad);
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = gg;
     }
+    for (size_t i = 4 * n4 + tid; i < n; i += nthreads)
+        adam_one(p[i], g[i], m[i], v[i], lr, b1, b2, eps, bc1, bc2_sqrt, zero_grad);
 }
 // device-resident step counter: t += 1, then the bias corrections of step t (double precision, like the host path)
 __global__ void adam_tick_k(int* t_dev, float* bc, float b1, float b2) {
@@ -1118,8 +1136,10 @@ int adam(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, f
          int zero_grad, const float* bias_corr_dev, cudaStream_t st) {
     if (n == 0) return SVAE_OK;
     const double bc1 = 1.0 - pow((double)b1, t > 0 ? t : 1), bc2 = 1.0 - pow((double)b2, t > 0 ? t : 1);
-    const int blocks = (int)min((size_t)148 * 16, (n + 255) / 256);
-    adam_k<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), zero_grad, bias_corr_dev);
+    const int blocks = (int)min((size_t)148 * 16, (n / 4 + 255) / 256 + 1);
+    const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    adam_k<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), zero_grad, bias_corr_dev, vec);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
@@ -1295,6 +1315,49 @@ __global__ void split3_k(const float* __restrict__ src, int rows, int cols, long
         d[0] = hi; d[seg] = t1; d[2 * seg] = t2;
     }
 }
+// four columns per thread: one 16-byte load (when the source row allows it) and three 8-byte stores.  cols_p is a
+// multiple of 64 in every caller, so the destination is always 8-byte aligned.
+__global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src, int rows, int cols, long ld,
+                                                   __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p, int kcat,
+                                                   int pattern, int src_vec) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = cols_p >> 2;
+    if (i >= (long)rows_p * c4) return;
+    const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        const float* sp = src + (long)r * ld + c;
+        if (src_vec && c + 3 < cols) {
+            const float4 v = *reinterpret_cast<const float4*>(sp);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? sp[e] : 0.f;
+        }
+    }
+    uint32_t hi2[2], lo2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * e] - __low2float(h), x[2 * e + 1] - __high2float(h));
+        hi2[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lo2[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint2 hi = make_uint2(hi2[0], hi2[1]), lo = make_uint2(lo2[0], lo2[1]);
+    const uint2 t1 = pattern == 0 ? hi : lo, t2 = pattern == 0 ? lo : hi;
+    if (kcat) {
+        __nv_bfloat16* d = dst + (long)r * 3 * cols_p + c;
+        *reinterpret_cast<uint2*>(d) = hi;
+        *reinterpret_cast<uint2*>(d + cols_p) = t1;
+        *reinterpret_cast<uint2*>(d + 2 * cols_p) = t2;
+    } else {
+        __nv_bfloat16* d = dst + (long)r * cols_p + c;
+        const long seg = (long)rows_p * cols_p;
+        *reinterpret_cast<uint2*>(d) = hi;
+        *reinterpret_cast<uint2*>(d + seg) = t1;
+        *reinterpret_cast<uint2*>(d + 2 * seg) = t2;
+    }
+}
 __global__ void act_backward_k(const float* __restrict__ out, const float* __restrict__ g, float* __restrict__ g_pre,
                                long n, int act) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1308,6 +1371,13 @@ int act_backward(const float* out, const float* g, float* g_pre, long n, int act
 
 int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, int rows_p, int cols_p, int kcat,
            int pattern, cudaStream_t st) {
+    if ((cols_p & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        const int src_vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ld % 4 == 0);
+        split3_v4_k<<<ceil_div((long)rows_p * (cols_p >> 2), 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat,
+                                                                                 pattern, src_vec);
+        SVAE_LAUNCH_CHECK();
+        return SVAE_OK;
+    }
     split3_k<<<ceil_div((long)rows_p * cols_p, 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat, pattern);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
