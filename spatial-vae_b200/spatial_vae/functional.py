@@ -481,6 +481,10 @@ def adam_step_graph(param, grad, m, v, lr, t_dev, bias_corr_dev, betas=(0.9, 0.9
 def gather_rows(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """src[index] for a 2-D+ fp32 dataset resident on the GPU (replaces the per-sample DataLoader fetch)."""
     _require_cuda(src, index)
+    if src.dtype != torch.float32:
+        raise ValueError(f"gather_rows fetches fp32 datasets, got {src.dtype}")
+    if not src.is_contiguous():
+        raise ValueError("gather_rows needs a contiguous dataset tensor")
     src2 = src.reshape(src.shape[0], -1)
     idx = index.to(torch.int64).contiguous()
     if out is None:
