@@ -31,3 +31,13 @@ busy = sum(v[0] for v in agg.values())
 print(f"20 steps: span {span/20:.1f} us/step, kernels busy {busy/20:.1f} us/step (sum of durations; overlap counts twice)")
 for k, (t, n) in sorted(agg.items(), key=lambda x: -x[1][0])[:32]:
     print(f"{t/20:9.1f} us/step x{n/20:5.1f}  {k}")
+
+# one step's timeline (start offset, duration, stream) when asked: python scripts/step_profile.py c2 graph timeline
+if len(sys.argv) > 3 and sys.argv[3] == "timeline":
+    starts = [i for i, e in enumerate(ev) if "gather_rows_k" in e.name]
+    a, b = starts[-2], starts[-1]
+    t0 = ev[a].time_range.start
+    print("\none step: start us | duration us | stream | kernel")
+    for e in ev[a:b]:
+        stream = getattr(e, "device_resource_id", None)
+        print(f"{e.time_range.start - t0:9.1f} {e.time_range.elapsed_us():8.1f}  s{stream}  {e.name[:90]}")
