@@ -147,6 +147,11 @@ typedef struct {
     const int32_t* rng_step;    /* device pointer to the step counter; required when eps == NULL  */
     uint64_t rng_seed;
     int64_t  rng_image_offset;  /* global minibatch index of this call's first image (this rank's slice) */
+    /* Optional cudaEvent_t (NULL = none), recorded by a training call at the point of its work where every DECODER
+     * parameter gradient is final, i.e. before the encoder backward (train_mnist.py:147 runs them in this order): a
+     * data-parallel caller waits for it on a second stream and starts reducing the decoder gradients while the
+     * encoder backward still runs.  Capturable: the event becomes a node of the caller's CUDA graph. */
+    void* decoder_grads_event;
 } SvaeStepInputs;
 
 /* Outputs of one eval_minibatch (all optional except stats). */

@@ -797,6 +797,12 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
             SVAE_TRY(latent_backward(s, c, d.f(p.S), p.Hp, d.f(p.img), dp.coord_w, s.Z > 0 ? d.f(p.dz) : nullptr, zo,
                                      eps, d.f(p.g_zo), st));
         }
+        if (in.decoder_grads_event != nullptr) {
+            // every decoder gradient is final once the parameter-gradient chain above is: it was forked from `st`
+            // after the last decoder kernel, so its stream (or `st` itself without one) is where the event goes
+            cudaStream_t s_ev = (side != nullptr && side->forked) ? side->aux : st;
+            SVAE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.decoder_grads_event), s_ev));
+        }
         if (gq) {
             enc_tc.side = side;
             if (enc_on_tc) SVAE_TRY(encoder_backward_tc(enc_tc, c.activation, qp, x_enc, d.f(p.g_zo), *gq, d.f(p.enc_scratch)));

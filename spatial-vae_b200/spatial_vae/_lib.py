@@ -55,7 +55,7 @@ class SvaeEncoderParams(C.Structure):
 
 class SvaeStepInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("grid", "y", "y_enc", "theta_offset", "eps", "ctf", "mask", "rng_step")] + \
-               [("rng_seed", C.c_uint64), ("rng_image_offset", C.c_int64)]
+               [("rng_seed", C.c_uint64), ("rng_image_offset", C.c_int64), ("decoder_grads_event", C.c_void_p)]
 
 
 class SvaeStepOutputs(C.Structure):

@@ -226,11 +226,13 @@ def shape_of(dec: DecoderTensors, enc: Sequence[tuple], B: int, P: int, Cin: int
 
 def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: torch.Tensor, y: torch.Tensor,
              eps: Optional[torch.Tensor], *, y_enc=None, theta_offset=None, ctf=None, mask=None, grad_dec=None,
-             grad_enc=None, grad_scale: Optional[float] = None, want_y_hat=False, want_latent=False, rng=None):
+             grad_enc=None, grad_scale: Optional[float] = None, want_y_hat=False, want_latent=False, rng=None,
+             decoder_grads_event: Optional["torch.cuda.Event"] = None):
     """Enqueue one svae_step.  Returns (stats (B,3), y_hat or None, latent or None).
     eps None: the library draws it in the kernel from rng = (seed, step_counter (int32 device tensor), global index of
     this call's first image): Philox keyed on (seed, step, global image index), independent of how a minibatch is split
-    across ranks."""
+    across ranks.  decoder_grads_event: a torch.cuda.Event the library records where every decoder gradient of this
+    call is final (before the encoder backward), for an early gradient exchange on another stream."""
     if eps is None and rng is None:
         raise ValueError("run_step needs eps or rng=(seed, step_tensor, image_offset)")
     _require_cuda(grid, y, dec.coord_w, enc[0][0], *([eps] if eps is not None else [rng[1]]))
@@ -272,6 +274,10 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
         if step_t.dtype != torch.int32:
             raise ValueError("rng step counter must be an int32 device tensor")
         inp.rng_step, inp.rng_seed, inp.rng_image_offset = step_t.data_ptr(), int(seed) & (2 ** 64 - 1), int(image_offset)
+    if decoder_grads_event is not None:
+        if not decoder_grads_event.cuda_event:
+            raise ValueError("decoder_grads_event has no CUDA handle yet: record it once before the first step")
+        inp.decoder_grads_event = decoder_grads_event.cuda_event
     stats = torch.empty(B, 3, dtype=torch.float32, device=dev)
     y_hat = torch.empty(B, P, shape.C, dtype=torch.float32, device=dev) if want_y_hat else None
     latent = torch.empty(B, shape.I, dtype=torch.float32, device=dev) if want_latent else None

@@ -160,6 +160,38 @@ def test_in_kernel_eps_is_standard_normal_and_split_invariant():
     assert abs((eps ** 3).mean()) < 0.1 and abs((eps ** 4).mean() - 3) < 0.2
 
 
+# ---- the hook for an early decoder-gradient exchange (reference order train_mnist.py:147) ----------------------
+def test_decoder_grads_event_marks_the_point_where_the_decoder_gradients_are_final():
+    """A second stream that waits for SvaeStepInputs.decoder_grads_event and snapshots the decoder's gradient tensors
+    sees their FINAL values (bit for bit), while the encoder backward is still to run on the main stream."""
+    dev = _cuda()
+    SF = _sf()
+    c, cfg, dec, enc, grid, y, eps = _config_case("c2", 64)
+    d, e, gd, ge = _dev_params(dec, enc, dev)
+    spec = SF.StepSpec(family="mnist", theta_prior=c["theta_prior"], precision="fast")
+    ev = torch.cuda.Event()
+    ev.record()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge, decoder_grads_event=ev)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        snap = [t.clone() for t in gd.flat()]
+    torch.cuda.synchronize()
+    assert ev.query()
+    for got, final in zip(snap, gd.flat()):
+        assert torch.equal(got, final)
+        assert torch.isfinite(final).all()
+    assert any(float(t.abs().max()) > 0 for t in gd.flat())
+    assert all(float(w.abs().max()) > 0 for w, _ in ge)
+    # an event that was never recorded may have no CUDA handle yet (torch creates it lazily): refused, not ignored
+    fresh = torch.cuda.Event()
+    if not fresh.cuda_event:
+        with pytest.raises(ValueError):
+            SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge,
+                        decoder_grads_event=fresh)
+
+
 # ---- ResidLinear.forward (reference models.py:13-21) ---------------------------------------------------------------------
 def test_resid_linear_module_forward_and_backward():
     import spatial_vae.models as M
