@@ -96,8 +96,8 @@ class Trainer:
         # Optional two-bucket gradient exchange on a GPU (SVAE_SPLIT_ALLREDUCE=1): the decoder's gradients are final
         # before the encoder backward starts (the library records an event there), so their allreduce runs on a second
         # stream under the encoder backward; the encoder's gradients and the loss sums follow on the main stream.
-        # Measured at C2 inside the captured graph: 1.706 -> 1.686 ms at 2 GPUs, 1.728 -> 1.743 ms at 8 (the second
-        # collective's latency outweighs the overlap), hence off by default: ONE allreduce per step.
+        # Measured at C2 inside the captured graph: 1.706 -> 1.686 ms at 2 GPUs, 1.728 -> 1.743 ms at 8 (one run; the
+        # second collective's latency costs what the overlap gains), hence off by default: ONE allreduce per step.
         import os
         self.split_allreduce = (self.world > 1 and dev.type == "cuda" and
                                 os.environ.get("SVAE_SPLIT_ALLREDUCE", "0") == "1")
