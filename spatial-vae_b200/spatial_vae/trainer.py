@@ -11,6 +11,7 @@ so state_dict()/torch.save keep working and Adam is a single kernel over the fla
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -98,7 +99,6 @@ class Trainer:
         # stream under the encoder backward; the encoder's gradients and the loss sums follow on the main stream.
         # Measured at C2 inside the captured graph: 1.706 -> 1.686 ms at 2 GPUs, 1.728 -> 1.743 ms at 8 (one run; the
         # second collective's latency costs what the overlap gains), hence off by default: ONE allreduce per step.
-        import os
         self.split_allreduce = (self.world > 1 and dev.type == "cuda" and
                                 os.environ.get("SVAE_SPLIT_ALLREDUCE", "0") == "1")
         self._comm = self._dec_ready = None
