@@ -159,6 +159,10 @@ typedef struct {
     float* stats;        /* (B, 3): per image [logp_i, kl_i, elbo_i]; the reference's scalars are their batch means */
     float* y_hat;        /* (B, P, C) decoder output or NULL                                   */
     float* latent;       /* (B, I) sampled latent or NULL                                      */
+    float* stats_sum;    /* (4) or NULL: [sum logp_i, sum kl_i, sum elbo_i, 0] over this call's images, WRITTEN (not
+                            accumulated) by one thread block in a fixed order: what train_mnist.py:153-160 accumulates
+                            on the host; a data-parallel caller points it at the tail of its gradient buffer so the
+                            loss sums ride in the gradient allreduce */
 } SvaeStepOutputs;
 
 int  svae_version(void);

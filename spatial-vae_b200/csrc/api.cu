@@ -747,6 +747,40 @@ __global__ void finalize_stats_k(float* stats, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) stats[b * 3 + 2] = stats[b * 3 + 0] - stats[b * 3 + 1];
 }
+// the same with the three column sums over the call's images written to sums[0..2] (sums[3] = 0): one block, so the
+// result is written, not accumulated, and its summation order is fixed
+__global__ void __launch_bounds__(1024) finalize_stats_sum_k(float* stats, int B, float* __restrict__ sums) {
+    __shared__ float red[3][32];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float lp = stats[b * 3 + 0], kl = stats[b * 3 + 1];
+        const float el = lp - kl;
+        stats[b * 3 + 2] = el;
+        a0 += lp; a1 += kl; a2 += el;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        a0 = lane < nw ? red[0][lane] : 0.f;
+        a1 = lane < nw ? red[1][lane] : 0.f;
+        a2 = lane < nw ? red[2][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) { sums[0] = a0; sums[1] = a1; sums[2] = a2; sums[3] = 0.f; }
+    }
+}
 
 template <typename T>
 static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, const SvaeDecoderParams& dp,
@@ -781,7 +815,8 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
     }
     Side* side = nullptr;
     if (train && (kFast || p.tc3)) SVAE_TRY(side_get(&side));
-    finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
+    if (out.stats_sum != nullptr) finalize_stats_sum_k<<<1, 1024, 0, st>>>(out.stats, s.B, out.stats_sum);
+    else finalize_stats_k<<<ceil_div(s.B, 128), 128, 0, st>>>(out.stats, s.B);
     SVAE_LAUNCH_CHECK();
     if (train) {
         if (p.opt) {

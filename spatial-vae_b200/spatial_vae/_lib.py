@@ -59,7 +59,7 @@ class SvaeStepInputs(C.Structure):
 
 
 class SvaeStepOutputs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("stats", "y_hat", "latent")]
+    _fields_ = [(n, C.c_void_p) for n in ("stats", "y_hat", "latent", "stats_sum")]
 
 
 def _load():

@@ -227,12 +227,13 @@ def shape_of(dec: DecoderTensors, enc: Sequence[tuple], B: int, P: int, Cin: int
 def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: torch.Tensor, y: torch.Tensor,
              eps: Optional[torch.Tensor], *, y_enc=None, theta_offset=None, ctf=None, mask=None, grad_dec=None,
              grad_enc=None, grad_scale: Optional[float] = None, want_y_hat=False, want_latent=False, rng=None,
-             decoder_grads_event: Optional["torch.cuda.Event"] = None):
+             decoder_grads_event: Optional["torch.cuda.Event"] = None, stats_sum: Optional[torch.Tensor] = None):
     """Enqueue one svae_step.  Returns (stats (B,3), y_hat or None, latent or None).
     eps None: the library draws it in the kernel from rng = (seed, step_counter (int32 device tensor), global index of
     this call's first image): Philox keyed on (seed, step, global image index), independent of how a minibatch is split
     across ranks.  decoder_grads_event: a torch.cuda.Event the library records where every decoder gradient of this
-    call is final (before the encoder backward), for an early gradient exchange on another stream."""
+    call is final (before the encoder backward), for an early gradient exchange on another stream.  stats_sum: a
+    contiguous fp32 device tensor of 4 elements that receives [sum logp, sum kl, sum elbo, 0] over the B images."""
     if eps is None and rng is None:
         raise ValueError("run_step needs eps or rng=(seed, step_tensor, image_offset)")
     _require_cuda(grid, y, dec.coord_w, enc[0][0], *([eps] if eps is not None else [rng[1]]))
@@ -283,6 +284,11 @@ def run_step(spec: StepSpec, dec: DecoderTensors, enc: Sequence[tuple], grid: to
     latent = torch.empty(B, shape.I, dtype=torch.float32, device=dev) if want_latent else None
     out = L.SvaeStepOutputs()
     out.stats, out.y_hat, out.latent = _ptr(stats), _ptr(y_hat), _ptr(latent)
+    if stats_sum is not None:
+        if stats_sum.dtype != torch.float32 or stats_sum.numel() != 4 or not stats_sum.is_contiguous() or \
+                stats_sum.device != dev:
+            raise ValueError("stats_sum must be a contiguous fp32 tensor of 4 elements on the step's device")
+        out.stats_sum = stats_sum.data_ptr()
 
     dstruct, estruct = dec.struct(), encoder_struct(enc)
     gd = grad_dec.struct() if grad_dec is not None else None

@@ -187,9 +187,13 @@ class Trainer:
             off = image_offset if image_offset is not None else self.rank * B_local
             rng = (self.seed, self.t_dev, off)          # t_dev: Adam's device-resident step counter (steps done so far)
         extra = {"decoder_grads_event": self._dec_ready} if self.split_allreduce else {}
-        stats, _, _ = SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc,
-                                  theta_offset=theta_offset, ctf=ctf, mask=mask, grad_dec=self.gdec,
-                                  grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1), rng=rng, **extra)
+        # the library writes this rank's three loss sums straight into the tail of the gradient buffer
+        tail = self.flat.grad_ext[self.flat.total:]
+        if B_local > 0:
+            extra["stats_sum"] = tail
+        SF.run_step(spec, self.dec, self.enc, x_coord, y_local, eps, y_enc=y_enc, theta_offset=theta_offset, ctf=ctf,
+                    mask=mask, grad_dec=self.gdec, grad_enc=self.genc, grad_scale=1.0 / max(B_global, 1), rng=rng,
+                    **extra)
         if self.split_allreduce:
             # first bucket: the decoder's gradients, on the second stream, as soon as the library's event fires (a
             # rank with an empty slice enqueued nothing: it joins the exchange after whatever the main stream holds)
@@ -200,10 +204,7 @@ class Trainer:
                 self._comm.wait_stream(main)
             with torch.cuda.stream(self._comm):
                 dist.all_reduce(self.flat.grad_ext[:self.n_dec_flat], op=dist.ReduceOp.SUM, group=self.pg)
-        tail = self.flat.grad_ext[self.flat.total:]
-        if B_local > 0:
-            tail[:3].copy_(stats.sum(0))
-        else:
+        if B_local == 0:
             tail.zero_()
         if self.split_allreduce:
             # second bucket: the encoder's gradients and the three loss sums

@@ -183,6 +183,13 @@ def test_trainer_runs_the_reference_loop_on_flat_buffers():
     for t in range(d["ys"].shape[0]):
         res = tr.step(grid, torch.from_numpy(d["ys"][t]).to(dev), eps=torch.from_numpy(d["eps"][t]).to(dev))
         np.testing.assert_allclose(float(res[0]), d["elbos"][t], rtol=1e-4)
+        np.testing.assert_allclose(float(res[0]), float(res[1]) - float(res[2]), rtol=1e-5)     # elbo = logp - kl
+    # the loss sums the step leaves in the tail of the gradient buffer are the column sums of the per-image stats
+    y0, eps0 = torch.from_numpy(d["ys"][0]).to(dev), torch.from_numpy(d["eps"][0]).to(dev)
+    sums = torch.full((4,), float("nan"), device=dev)
+    stats, _, _ = SF.run_step(spec, tr.dec, tr.enc, grid, y0, eps0, stats_sum=sums)
+    np.testing.assert_allclose(sums[:3].cpu().numpy(), stats.sum(0).cpu().numpy(), rtol=1e-5)
+    assert float(sums[3]) == 0.0
     for k, v in p.state_dict().items():
         assert float((v.cpu() - torch.from_numpy(d["final.p." + k])).abs().max()) < 1e-4, k
     for k, v in q.state_dict().items():
