@@ -160,7 +160,7 @@ typedef struct {
     float* y_hat;        /* (B, P, C) decoder output or NULL                                   */
     float* latent;       /* (B, I) sampled latent or NULL                                      */
     float* stats_sum;    /* (4) or NULL: [sum logp_i, sum kl_i, sum elbo_i, 0] over this call's images, WRITTEN (not
-                            accumulated) by one thread block in a fixed order: what train_mnist.py:153-160 accumulates
+                            accumulated) by one thread block in a fixed order: what train_mnist.py:152-165 accumulates
                             on the host; a data-parallel caller points it at the tail of its gradient buffer so the
                             loss sums ride in the gradient allreduce */
 } SvaeStepOutputs;
