@@ -5,8 +5,8 @@ into _build/ with
   * kernel<<<grid, block, smem, stream>>>(args)   ->  svae_emu::Launcher(grid, block, smem, stream).run(kernel, args)
   * extern __shared__ T name[];                   ->  T* name = (T*)svae_emu::dyn_smem();
   * the two inline-PTX statements (tanh.approx, %globaltimer) -> tanhf / the host clock
-and compiles them with g++ against cuda_emu.h.  tc_gemm.cu (tcgen05 / TMEM / TMA) cannot run on a host and is
-replaced by the plain-loop stand-in tc_gemm_ref.cpp.
+and compiles them with g++ against cuda_emu.h.  tc_gemm.cu and tc_bwd.cu (tcgen05 / TMEM / TMA) run on the host model
+of those units in tc_emu.h, which replaces the PTX-wrapper section of tc_ptx.cuh.
 """
 import os
 import re
@@ -17,12 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "spatial-vae_b200", "csrc")
 ASAN = os.environ.get("SVAE_EMU_ASAN") == "1"      # out-of-bounds hunting: run python with LD_PRELOAD=libasan.so
-BUILD = os.path.join(HERE, ("_build_asan" if ASAN else "_build") + ("" if os.environ.get("SVAE_EMU_TC", "kernel") != "ref" else "_ref"))
+BUILD = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 OUT = os.path.join(BUILD, "libsvae_emu.so")
 SOURCES = ["api.cu", "sgemm.cu", "step_kernels.cu", "option_kernels.cu", "ingest_kernels.cu"]
-# SVAE_EMU_TC=kernel (default): tc_gemm.cu itself runs on the host model of tcgen05 / TMA / mbarriers (tc_emu.h);
-# SVAE_EMU_TC=ref: the plain-loop stand-in tc_gemm_ref.cpp (much faster, exercises only the call sequence)
-TC_KERNEL = os.environ.get("SVAE_EMU_TC", "kernel") != "ref"
 HEADERS = ["common.cuh", "kernels.cuh", "first_layer.cuh"]
 # tensor-core kernel sources and the number of inline red.global.add.v4.f32 statements each contains
 TC_SOURCES = {"tc_gemm.cu": 1, "tc_bwd.cu": 1}
@@ -71,7 +68,7 @@ def newest(paths):
 def build(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     inputs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + list(TC_SOURCES) + ["tc_ptx.cuh"]] + \
-             [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc_gemm_ref.cpp", "tc_emu.h", "build.py",
+             [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "tc_emu.h", "build.py",
                                               "include/cuda.h")] + \
              [os.path.join(ROOT, "include", "svae_b200.h")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest(inputs):
@@ -86,16 +83,13 @@ def build(force: bool = False) -> str:
             dst.write(rewrite(src.read()))
         units.append(out)
     units.append(os.path.join(HERE, "cuda_emu.cpp"))
-    if TC_KERNEL:
-        with open(os.path.join(CSRC, "tc_ptx.cuh")) as src, open(os.path.join(BUILD, "tc_ptx.cuh"), "w") as dst:
-            dst.write(rewrite(rewrite_tc_header(src.read())))
-        for f, n_red in TC_SOURCES.items():
-            out = os.path.join(BUILD, f.replace(".cu", ".cpp"))
-            with open(os.path.join(CSRC, f)) as src, open(out, "w") as dst:
-                dst.write(rewrite(rewrite_tc(src.read(), n_red)))
-            units.append(out)
-    else:
-        units.append(os.path.join(HERE, "tc_gemm_ref.cpp"))
+    with open(os.path.join(CSRC, "tc_ptx.cuh")) as src, open(os.path.join(BUILD, "tc_ptx.cuh"), "w") as dst:
+        dst.write(rewrite(rewrite_tc_header(src.read())))
+    for f, n_red in TC_SOURCES.items():
+        out = os.path.join(BUILD, f.replace(".cu", ".cpp"))
+        with open(os.path.join(CSRC, f)) as src, open(out, "w") as dst:
+            dst.write(rewrite(rewrite_tc(src.read(), n_red)))
+        units.append(out)
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
              "-I", os.path.join(HERE, "include"), "-I", BUILD, "-I", HERE]
     link = []
