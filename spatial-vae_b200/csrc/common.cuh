@@ -106,9 +106,13 @@ struct TcExtra {
     const float* out_w = nullptr; int out_w_ld = 0; int dot_c = 0; float* o_accum = nullptr;
     // modes 0/1: fp32 output (and fp32 aux) instead of bf16
     int out_f32 = 0;
+    // mode 0 with out_f32: split K over the CTA pairs that would otherwise idle and ADD the raw partial sums to `out`
+    // with fp32 atomics (no bias, no activation; zero `out` first and finish the layer with split3_act)
+    int raw_split_k = 0;
     // mode 0: ResidLinear (models.py:13-21): out = act(A W^T + bias + resid), resid (M x N, bf16, ld elements)
     const void* resid = nullptr; int ld_resid = 0;
 };
+int tc_split_k_factor(int M, int N);      // CTA pairs (or CTAs) per output tile of an M x N forward GEMM
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
             int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st,
             const TcExtra& ex = TcExtra());

@@ -1317,9 +1317,13 @@ __global__ void split3_k(const float* __restrict__ src, int rows, int cols, long
 }
 // four columns per thread: one 16-byte load (when the source row allows it) and three 8-byte stores.  cols_p is a
 // multiple of 64 in every caller, so the destination is always 8-byte aligned.
+// FINISH: src holds the RAW sums of a K-split GEMM (ld = cols_p, 16-byte aligned); h = act(src + bias) goes back in
+// place (padded columns: act(0), what the fused GEMM epilogue writes there) before it is split; dst may be NULL.
+template <bool FINISH>
 __global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src, int rows, int cols, long ld,
                                                    __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p, int kcat,
-                                                   int pattern, int src_vec) {
+                                                   int pattern, int src_vec, const float* __restrict__ bias, int act,
+                                                   float* act_out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c4 = cols_p >> 2;
     if (i >= (long)rows_p * c4) return;
@@ -1327,7 +1331,18 @@ __global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src
     float x[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < rows) {
         const float* sp = src + (long)r * ld + c;
-        if (src_vec && c + 3 < cols) {
+        if (FINISH) {
+            const float4 v = *reinterpret_cast<const float4*>(sp);
+            const float raw[4] = {v.x, v.y, v.z, v.w};
+            float h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool live = c + e < cols;
+                h[e] = act_apply<false>(act, live ? raw[e] + (bias != nullptr ? __ldg(bias + c + e) : 0.f) : 0.f);
+                x[e] = live ? h[e] : 0.f;
+            }
+            *reinterpret_cast<float4*>(act_out + (long)r * ld + c) = make_float4(h[0], h[1], h[2], h[3]);
+        } else if (src_vec && c + 3 < cols) {
             const float4 v = *reinterpret_cast<const float4*>(sp);
             x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
         } else {
@@ -1335,6 +1350,7 @@ __global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src
             for (int e = 0; e < 4; ++e) x[e] = (c + e < cols) ? sp[e] : 0.f;
         }
     }
+    if (FINISH && dst == nullptr) return;
     uint32_t hi2[2], lo2[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -1373,12 +1389,25 @@ int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, in
            int pattern, cudaStream_t st) {
     if ((cols_p & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         const int src_vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ld % 4 == 0);
-        split3_v4_k<<<ceil_div((long)rows_p * (cols_p >> 2), 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat,
-                                                                                 pattern, src_vec);
+        split3_v4_k<false><<<ceil_div((long)rows_p * (cols_p >> 2), 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat,
+                                                                                        pattern, src_vec, nullptr, -1, nullptr);
         SVAE_LAUNCH_CHECK();
         return SVAE_OK;
     }
     split3_k<<<ceil_div((long)rows_p * cols_p, 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat, pattern);
+    SVAE_LAUNCH_CHECK();
+    return SVAE_OK;
+}
+
+int split3_act(float* raw, const float* bias, int act, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p,
+               int kcat, int pattern, cudaStream_t st) {
+    SVAE_REQUIRE((cols_p & 3) == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+                 (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 7) == 0) && rows_p >= rows, SVAE_EALIGN,
+                 "split3_act: the raw sums must be 16-byte aligned rows of a multiple of 4 columns");
+    // without a split destination only the live rows are finished
+    const int rp = dst != nullptr ? rows_p : rows;
+    split3_v4_k<true><<<ceil_div((long)rp * (cols_p >> 2), 256), 256, 0, st>>>(raw, rows, cols, cols_p, dst, rp, cols_p, kcat,
+                                                                              pattern, 1, bias, act, raw);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }

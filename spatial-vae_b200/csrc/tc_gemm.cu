@@ -78,6 +78,8 @@ struct TcParams {
     int vec_red;              // mode 2: 16-byte aligned rows -> red.global.add.v4.f32
     int out_f32;              // modes 0/1: fp32 output (and fp32 aux) instead of bf16
     int res;                  // mode 0: a bf16 residual tile is added before the activation (ResidLinear)
+    int raw;                  // mode 0, fp32 output: K is split over CTAs and the RAW partial sums are added to `out`
+                              // with atomics (no bias, no activation): the caller zeroes `out` and finishes the layer
     // mode 0, optional: fused output layer (models.py:84): o_accum[m, c] += sum_n h[m,n] * out_w[c, n]
     const float* out_w; int out_w_ld; int dot_c; float* o_accum;
 };
@@ -237,8 +239,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         };
-        if (MODE == 2) {
-            // fp32 partial dW tile -> global atomics; group g takes the 32-column chunks c/32 == g (mod EG)
+        if (MODE == 2 || (MODE == 0 && OUT32 && p.raw)) {
+            // fp32 partial tile (dW, or a K split of an fp32-output forward) -> global atomics; group g takes the
+            // 32-column chunks c/32 == g (mod EG)
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int mt = mn / p.n_tiles, nt = mn % p.n_tiles;
@@ -511,6 +514,13 @@ int launch_act(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
 
 }  // namespace
 
+// how many ways the K loop of an M x N forward can be split so that every CTA (pair) gets a tile
+int tc_split_k_factor(int M, int N) {
+    const int cg = cta_group_size();
+    const int tiles = ceil_div(M, BM * cg) * ceil_div(N, BN);
+    return tiles > 0 ? (sm_count() / cg) / tiles : 1;
+}
+
 int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias,
             int bias_n, const void* aux, int ldaux, int act, void* out, int ldo, cudaStream_t st, const TcExtra& ex) {
     SVAE_REQUIRE(mode >= 0 && mode <= 2, SVAE_EINVAL, "tc_gemm: unknown mode %d", mode);
@@ -522,6 +532,7 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
     p.out_w = ex.out_w; p.out_w_ld = ex.out_w_ld; p.dot_c = ex.dot_c; p.o_accum = ex.o_accum;
     p.out_f32 = (ex.out_f32 && mode != 2) ? 1 : 0;
     p.res = (mode == 0 && ex.resid != nullptr) ? 1 : 0;
+    p.raw = (mode == 0 && p.out_f32 && ex.raw_split_k) ? 1 : 0;
     const bool f32 = p.out_f32 != 0;
     const uint32_t ebox = f32 ? 32 : 64;          // epilogue block: 128 bytes of columns
     const int cg = cta_group_size();
@@ -558,6 +569,16 @@ int tc_gemm(int mode, int M, int N, int K, const void* A, int lda, const void* W
         // A: (K rows) x (lda cols) with M <= lda logical columns; Bm: (K rows) x (ldw cols), N <= ldw
         SVAE_TRY(make_map(&ma, A, K, round_up(M, 64) <= lda ? round_up(M, 64) : lda, lda, 64, 64));
         SVAE_TRY(make_map(&mb, W, K, round_up(N, 64) <= ldw ? round_up(N, 64) : ldw, ldw, 64, 64));
+        const int mn = p.m_tiles * p.n_tiles;
+        int splits = (sms / cg) / mn;
+        if (splits < 1) splits = 1;
+        if (splits > p.k_blocks) splits = p.k_blocks;
+        p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
+        p.k_splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
+        p.vec_red = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    }
+    if (p.raw) {
+        // few output tiles walking a long K (the encoder's small-batch GEMMs): split K over the idle CTA pairs
         const int mn = p.m_tiles * p.n_tiles;
         int splits = (sms / cg) / mn;
         if (splits < 1) splits = 1;

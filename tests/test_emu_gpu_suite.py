@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # The tcgen05 GEMM unit tests and the C1-shape step in FAST precision (H = 500, two n-tiles, fused output dot) DO run:
 # tc_gemm.cu itself executes on the host model of tcgen05 / TMA / mbarriers (tests/simt_emu/tc_emu.h).
 DESELECT = ("not (c1_shape and parity) and not c2_full_size and not full_model_size and not graphed_step "
-            "and not baseline_model_shapes and not in_kernel_eps and not trajectory_at_c1 and not decoder_grads_event")
+            "and not baseline_model_shapes and not in_kernel_eps and not trajectory_at_c1 and not decoder_grads_event and not small_and_large_batch")
 
 
 def test_gpu_test_bodies_pass_on_the_simt_emulation():

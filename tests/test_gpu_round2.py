@@ -102,6 +102,38 @@ def test_baseline_model_shapes_match_the_oracle(name, B, precision, tol, gtol):
         assert float((a - b).abs().max()) <= gtol * scale, (name, precision, i, float((a - b).abs().max()) / scale)
 
 
+@pytest.mark.parametrize("precision,tol,gtol", [("fast", 1e-3, 0.05), ("parity_tc", 2e-5, 2e-3)])
+def test_encoder_gemm_epilogues_small_and_large_batch(precision, tol, gtol):
+    """The inference network's tensor-core GEMMs (models.py:46-54) finish a layer in two ways: with few output tiles
+    (every benchmark minibatch) K is split over the idle CTA pairs and bias + activation are applied by the next
+    kernel; with more tiles than half the GPU the GEMM's own epilogue does it.  A tiny model at 64 and at 9 600 images
+    takes one path each; both against the CPU oracle."""
+    dev = _cuda()
+    SF = _sf()
+    from spatial_vae import _lib as L
+    n, H, Hq, Z = 4, 32, 64, 2
+    P = n * n
+    for B in (64, 9600):
+        dec, enc = O.init_params(P, Z + 3, Z, H, 2, Hq, 2, 1, seed=5)
+        g = torch.Generator().manual_seed(B)
+        y = torch.rand(B, P, generator=g)
+        eps = torch.randn(B, Z + 3, generator=g)
+        cfg = O.StepConfig(family="mnist", theta_prior=math.pi / 4)
+        grid = O.make_grid(n, n)
+        out, ograds = O.step_grads(cfg, dec, enc, grid, y, eps)
+        ref = (out["logp_i"] - out["kl_i"]).numpy()
+        d, e, gd, ge = _dev_params(dec, enc, dev)
+        spec = SF.StepSpec(family="mnist", theta_prior=math.pi / 4, precision=precision, activation=L.ACT_TANH)
+        stats, _, _ = SF.run_step(spec, d, e, grid.to(dev), y.to(dev), eps.to(dev), grad_dec=gd, grad_enc=ge)
+        torch.cuda.synchronize()
+        rel = np.abs(stats[:, 2].cpu().numpy() - ref) / np.abs(ref)
+        assert rel.max() <= tol, (B, precision, rel.max())
+        grads = [t.cpu() for t in gd.flat()] + [t.cpu() for pr in ge for t in pr]
+        for i, (a, b) in enumerate(zip(grads, ograds)):
+            scale = max(float(b.abs().max()), 1e-12)
+            assert float((a - b).abs().max()) <= gtol * scale, (B, precision, i, float((a - b).abs().max()) / scale)
+
+
 def test_parity_tc_matches_parity_on_a_golden_step():
     """The tensor-core parity mode against the reference-written fixture, at the PARITY tolerances."""
     from tests.helpers import cfg_of, golden_grads, load_case, oracle_params
