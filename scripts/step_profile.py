@@ -11,7 +11,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
 c = dict(bench.CONFIGS[name])
 dev = torch.device("cuda", 0)
-w = bench.Workload(name, c, dev, 0, 1, "fast")
+precision = os.environ.get("SVAE_PROFILE_PRECISION", "fast")     # fast | parity_tc | parity
+w = bench.Workload(name, c, dev, 0, 1, precision)
 fn = w.trainer.step_graphed if use_graph else w.trainer.step
 for _ in range(30):
     w.device_step(fn)
