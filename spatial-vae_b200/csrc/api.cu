@@ -486,12 +486,12 @@ int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& 
     const int H = d.s->H, Hp = d.p->Hp;
     if (d.p->tc3) {
         // dW_l += delta^T act[l-1]: the three terms stacked along the reduction dimension (rows)
-        SVAE_TRY(split3(delta, rows, H, Hp, d.b16(d.p->d_gs), rows, Hp, 0, 0, d.st));
+        // (delta is split ONCE: row-stacked for this GEMM, K-concatenated for the dX GEMM below)
+        SVAE_TRY(split3_both(delta, rows, H, Hp, d.b16(d.p->d_gs), d.b16(d.p->d_xs), rows, Hp, 0, d.st));
         SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, d.b16(d.p->d_as), rows, Hp, 0, 1, d.st));
         SVAE_TRY(tc_gemm(2, H, H, 3 * rows, d.b16(d.p->d_gs), Hp, d.b16(d.p->d_as), Hp, nullptr, 0, nullptr, 0, -1,
                          g.hidden_w[l - 1], H, d.st));
         // delta_prev = (delta W_l) .* act'(act[l-1])
-        SVAE_TRY(split3(delta, rows, H, Hp, d.b16(d.p->d_xs), rows, Hp, 1, 0, d.st));
         TcExtra f32out;
         f32out.out_f32 = 1;
         return tc_gemm(1, rows, Hp, 3 * Hp, d.b16(d.p->d_xs), 3 * Hp, reinterpret_cast<__nv_bfloat16*>(d.ws + d.p->d_wr[l - 1]),
