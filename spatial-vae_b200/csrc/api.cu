@@ -434,6 +434,8 @@ struct DecoderCtx {
     __nv_bfloat16* b16(size_t off) const { return reinterpret_cast<__nv_bfloat16*>(ws + off); }
     // operand of the dX GEMM of hidden layer l+1: W, or the W + I copy for ResidLinear layers on tensor cores
     __nv_bfloat16* wbf_dx(int l) const { return wbf(p->resid_tc ? (s->L - 1) + l : l); }
+    bool bwd_follows = false;        // set by the callers that run decoder_chunk_backward after the forward
+    bool fwd_splits_for_bwd() const { return bwd_follows && p->tc3 && s->L == 2; }
     // first-layer coordinate weights of image 0: W_eff (B, H*F) with bilinear, else coord_linear.weight
     const float* l0_w(const SvaeDecoderParams& dp) const { return c->bilinear ? f(p->weff) : dp.coord_w; }
 };
@@ -448,7 +450,12 @@ int hidden_forward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& d
         // act[l] = act(act[l-1] W^T + b): operands split into (hi, hi, lo) x (hi, lo, hi) bf16 terms along K
         __nv_bfloat16* xs = d.b16(d.p->d_xs);
         __nv_bfloat16* wk = reinterpret_cast<__nv_bfloat16*>(d.ws + d.p->d_wk[l - 1]);
-        SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, xs, rows, Hp, 1, 0, d.st));
+        // a backward over the same chunk follows and there is one hidden GEMM: its dW operand (the same matrix,
+        // row-stacked, B-side terms) is written in the same pass
+        if (d.fwd_splits_for_bwd())
+            SVAE_TRY(split3_both(d.act(l - 1), rows, H, Hp, d.b16(d.p->d_as), 1, xs, 0, rows, Hp, d.st));
+        else
+            SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, xs, rows, Hp, 1, 0, d.st));
         TcExtra f32out;
         f32out.out_f32 = 1;
         return tc_gemm(0, rows, Hp, 3 * Hp, xs, 3 * Hp, wk, 3 * Hp, dp.hidden_b[l - 1], H, nullptr, 0, d.c->activation,
@@ -487,8 +494,10 @@ int hidden_backward<float>(const DecoderCtx<float>& d, const SvaeDecoderParams& 
     if (d.p->tc3) {
         // dW_l += delta^T act[l-1]: the three terms stacked along the reduction dimension (rows)
         // (delta is split ONCE: row-stacked for this GEMM, K-concatenated for the dX GEMM below)
-        SVAE_TRY(split3_both(delta, rows, H, Hp, d.b16(d.p->d_gs), d.b16(d.p->d_xs), rows, Hp, 0, d.st));
-        SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, d.b16(d.p->d_as), rows, Hp, 0, 1, d.st));
+        SVAE_TRY(split3_both(delta, rows, H, Hp, d.b16(d.p->d_gs), 0, d.b16(d.p->d_xs), 0, rows, Hp, d.st));
+        // (with two hidden layers the forward already left act[l-1] here, see hidden_forward)
+        if (!d.fwd_splits_for_bwd())
+            SVAE_TRY(split3(d.act(l - 1), rows, H, Hp, d.b16(d.p->d_as), rows, Hp, 0, 1, d.st));
         SVAE_TRY(tc_gemm(2, H, H, 3 * rows, d.b16(d.p->d_gs), Hp, d.b16(d.p->d_as), Hp, nullptr, 0, nullptr, 0, -1,
                          g.hidden_w[l - 1], H, d.st));
         // delta_prev = (delta W_l) .* act'(act[l-1])
@@ -818,6 +827,7 @@ static int step_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, con
                      SvaeDecoderParams* gd, SvaeEncoderParams* gq, char* ws, cudaStream_t st) {
     DecoderCtx<T> d{&s, &c, &p, ws, st};
     const bool train = (gd != nullptr);
+    d.bwd_follows = train;
     const float* x_enc = in.y_enc ? in.y_enc : in.y;
     float* zo = d.f(p.zo);
     constexpr bool kFast = !std::is_same<T, float>::value;
@@ -905,6 +915,7 @@ static int decoder_impl(const SvaeShape& s, const SvaeConfig& c, const Plan& p, 
                         const float* x, const float* z, float* y_hat, const float* g_y, SvaeDecoderParams* gd,
                         float* g_x, float* g_z, char* ws, cudaStream_t st) {
     DecoderCtx<T> d{&s, &c, &p, ws, st};
+    d.bwd_follows = (gd != nullptr);
     if (s.B == 0) return SVAE_OK;
     if (s.Z > 0) {
         scale_rows_k<<<ceil_div((long)s.B * s.Z, 256), 256, 0, st>>>(z, d.f(p.zs), (long)s.B * s.Z, 1.f);

@@ -119,9 +119,10 @@ int clock_probe(float* out_mhz, cudaStream_t st);
 // fp32 -> (hi, hi|lo, lo|hi) bf16 terms for the 3-MMA error-compensated encoder GEMMs (see step_kernels.cu)
 int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, int rows_p, int cols_p, int kcat,
            int pattern, cudaStream_t st);
-// one pass over src writing both layouts (same terms): dst_r row-stacked (kcat = 0), dst_k K-concatenated (kcat = 1)
-int split3_both(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst_r, __nv_bfloat16* dst_k, int rows_p,
-                int cols_p, int pattern, cudaStream_t st);
+// one pass over src writing both layouts: dst_r row-stacked (kcat = 0) with the terms of pattern_r, dst_k
+// K-concatenated (kcat = 1) with those of pattern_k
+int split3_both(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst_r, int pattern_r, __nv_bfloat16* dst_k,
+                int pattern_k, int rows_p, int cols_p, cudaStream_t st);
 // the same after finishing a layer whose GEMM left RAW sums in `raw` (rows x cols_p fp32, ld = cols_p):
 // h = act(raw + bias) is written back IN PLACE (padded columns: act(0)) and split into dst (dst NULL: no split)
 int split3_act(float* raw, const float* bias, int act, int rows, int cols, __nv_bfloat16* dst, int rows_p, int cols_p,

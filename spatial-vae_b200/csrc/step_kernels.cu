@@ -1323,7 +1323,8 @@ template <bool FINISH>
 __global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src, int rows, int cols, long ld,
                                                    __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p, int kcat,
                                                    int pattern, int src_vec, const float* __restrict__ bias, int act,
-                                                   float* act_out, __nv_bfloat16* __restrict__ dst_alt) {
+                                                   float* act_out, __nv_bfloat16* __restrict__ dst_alt,
+                                                   int pattern_alt) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c4 = cols_p >> 2;
     if (i >= (long)rows_p * c4) return;
@@ -1360,22 +1361,22 @@ __global__ void __launch_bounds__(256) split3_v4_k(const float* __restrict__ src
         lo2[e] = *reinterpret_cast<const uint32_t*>(&l);
     }
     const uint2 hi = make_uint2(hi2[0], hi2[1]), lo = make_uint2(lo2[0], lo2[1]);
-    const uint2 t1 = pattern == 0 ? hi : lo, t2 = pattern == 0 ? lo : hi;
-    // dst in the requested layout; dst_alt (optional) receives the same terms in the other one
+    // dst in the requested layout; dst_alt (optional) receives the terms of pattern_alt in the other one
     __nv_bfloat16* dk = kcat ? dst : dst_alt;
     __nv_bfloat16* dr = kcat ? dst_alt : dst;
+    const int pk = kcat ? pattern : pattern_alt, pr = kcat ? pattern_alt : pattern;
     if (dk != nullptr) {
         __nv_bfloat16* d = dk + (long)r * 3 * cols_p + c;
         *reinterpret_cast<uint2*>(d) = hi;
-        *reinterpret_cast<uint2*>(d + cols_p) = t1;
-        *reinterpret_cast<uint2*>(d + 2 * cols_p) = t2;
+        *reinterpret_cast<uint2*>(d + cols_p) = pk == 0 ? hi : lo;
+        *reinterpret_cast<uint2*>(d + 2 * cols_p) = pk == 0 ? lo : hi;
     }
     if (dr != nullptr) {
         __nv_bfloat16* d = dr + (long)r * cols_p + c;
         const long seg = (long)rows_p * cols_p;
         *reinterpret_cast<uint2*>(d) = hi;
-        *reinterpret_cast<uint2*>(d + seg) = t1;
-        *reinterpret_cast<uint2*>(d + 2 * seg) = t2;
+        *reinterpret_cast<uint2*>(d + seg) = pr == 0 ? hi : lo;
+        *reinterpret_cast<uint2*>(d + 2 * seg) = pr == 0 ? lo : hi;
     }
 }
 __global__ void act_backward_k(const float* __restrict__ out, const float* __restrict__ g, float* __restrict__ g_pre,
@@ -1394,7 +1395,7 @@ int split3(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst, in
     if ((cols_p & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         const int src_vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ld % 4 == 0);
         split3_v4_k<false><<<ceil_div((long)rows_p * (cols_p >> 2), 256), 256, 0, st>>>(src, rows, cols, ld, dst, rows_p, cols_p, kcat,
-                                                                                        pattern, src_vec, nullptr, -1, nullptr, nullptr);
+                                                                                        pattern, src_vec, nullptr, -1, nullptr, nullptr, pattern);
         SVAE_LAUNCH_CHECK();
         return SVAE_OK;
     }
@@ -1411,19 +1412,21 @@ int split3_act(float* raw, const float* bias, int act, int rows, int cols, __nv_
     // without a split destination only the live rows are finished
     const int rp = dst != nullptr ? rows_p : rows;
     split3_v4_k<true><<<ceil_div((long)rp * (cols_p >> 2), 256), 256, 0, st>>>(raw, rows, cols, cols_p, dst, rp, cols_p, kcat,
-                                                                              pattern, 1, bias, act, raw, nullptr);
+                                                                              pattern, 1, bias, act, raw, nullptr, pattern);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
 
-// one pass over src, both layouts: dst_r (3*rows_p, cols_p) row-stacked and dst_k (rows_p, 3*cols_p) K-concatenated
-int split3_both(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst_r, __nv_bfloat16* dst_k, int rows_p,
-                int cols_p, int pattern, cudaStream_t st) {
+// one pass over src, both layouts: dst_r (3*rows_p, cols_p) row-stacked with the terms of pattern_r and dst_k
+// (rows_p, 3*cols_p) K-concatenated with those of pattern_k
+int split3_both(const float* src, int rows, int cols, long ld, __nv_bfloat16* dst_r, int pattern_r, __nv_bfloat16* dst_k,
+                int pattern_k, int rows_p, int cols_p, cudaStream_t st) {
     SVAE_REQUIRE((cols_p & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_r) & 7) == 0 &&
                  (reinterpret_cast<uintptr_t>(dst_k) & 7) == 0, SVAE_EALIGN, "split3_both: unaligned destination");
     const int src_vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (ld % 4 == 0);
     split3_v4_k<false><<<ceil_div((long)rows_p * (cols_p >> 2), 256), 256, 0, st>>>(src, rows, cols, ld, dst_r, rows_p, cols_p, 0,
-                                                                                    pattern, src_vec, nullptr, -1, nullptr, dst_k);
+                                                                                    pattern_r, src_vec, nullptr, -1, nullptr, dst_k,
+                                                                                    pattern_k);
     SVAE_LAUNCH_CHECK();
     return SVAE_OK;
 }
