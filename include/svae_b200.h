@@ -36,7 +36,9 @@
  *     graph simply gets parallel branches.
  *   - accumulated outputs (gradient buffers, `+=` in the text below) are summed with fp32 atomics across thread
  *     blocks: the summation ORDER, hence the last bits of a gradient, can differ between two runs on the same input
- *     (|difference| ~ 1e-7 relative; the reference's cuBLAS split-K GEMMs behave the same way).
+ *     (|difference| ~ 1e-7 relative; the reference's cuBLAS split-K GEMMs behave the same way).  The inference
+ *     network's small-batch GEMMs split K over thread blocks in the same manner (hidden layers in FAST / PARITY_TC,
+ *     the head in every precision), so the per-image statistics carry the same last-bit variation.
  *   - svae_step / svae_decoder_* walk the minibatch in chunks of whole images sized so that the activation part of the
  *     workspace stays near 6 GiB (cfg.chunk_images = 0) or in chunks of cfg.chunk_images; svae_workspace_bytes()
  *     reports the size for that choice, results do not depend on it, and a workspace smaller than reported is
